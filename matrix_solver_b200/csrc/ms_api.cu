@@ -1,0 +1,1096 @@
+// ms_api.cu — the C ABI (include/ms_b200.h) and the host-side orchestration of the blocked
+// right-looking R^T D R factorisation and the two triangular sweeps.
+//
+// Factorisation (replaces the left-looking loop of src/solver.cpp:8-104).  For block row I:
+//   panel stream : pretest (src/solver.cpp:117) -> for every 64-row piece of the block row:
+//                  diag kernel (K1+K2) -> panel kernel (K3: in place + panel buffer) -> update of the
+//                  later pieces of the same block row (K = 64)
+//                  -> [nranks > 1] ncclBroadcast of the panel buffer and of d_I from the owner
+//   main stream  : rank-m update (K4+K5) of block row I+1 first, then of all later block rows.
+// Look-ahead: the panel stream starts block row I+1 as soon as ITS rows have received update I,
+// while the main stream is still applying update I to the rest (two panel buffers alternate).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "ms_common.cuh"
+#include "ms_nccl.h"
+
+static thread_local char g_err[1024] = "";
+
+void
+ms_set_error (const char *fmt, ...)
+{
+  va_list ap;
+  va_start (ap, fmt);
+  vsnprintf (g_err, sizeof (g_err), fmt, ap);
+  va_end (ap);
+}
+
+extern "C" const char *
+ms_last_error (void)
+{
+  return g_err;
+}
+
+extern "C" int
+ms_device_count (int *count)
+{
+  MS_CHECK_ARG (count != nullptr, "count is null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount (&n);
+  if (e != cudaSuccess)
+    {
+      cudaGetLastError ();
+      n = 0;
+    }
+  *count = n;
+  return MS_OK;
+}
+
+static int
+require_device (int device)
+{
+  int n = 0;
+  if (cudaGetDeviceCount (&n) != cudaSuccess || n == 0)
+    {
+      cudaGetLastError ();
+      ms_set_error ("no CUDA device visible: this library has no CPU fallback");
+      return MS_ERR_NO_DEVICE;
+    }
+  if (device < 0 || device >= n)
+    {
+      ms_set_error ("device %d out of range (%d visible)", device, n);
+      return MS_ERR_NO_DEVICE;
+    }
+  cudaDeviceProp prop;
+  MS_CUDA (cudaGetDeviceProperties (&prop, device));
+  if (prop.major != 10)
+    {
+      ms_set_error ("device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major,
+                    prop.minor);
+      return MS_ERR_NO_DEVICE;
+    }
+  MS_CUDA (cudaSetDevice (device));
+  return MS_OK;
+}
+
+// ----------------------------------------------------------------------------- lifetime
+constexpr size_t MS_STAGE_DOUBLES = (size_t)4 << 20;  // 32 MB staging halves
+
+static void
+build_pieces (ms_ctx *c)
+{
+  c->pieces.clear ();
+  c->block_first_piece.assign (c->nblocks + 1, 0);
+  for (size_t I = 0; I < c->nblocks; I++)
+    {
+      c->block_first_piece[I] = c->pieces.size ();
+      size_t rows = c->block_rows (I);
+      for (size_t off = 0; off < rows; off += MS_SUB)
+        {
+          ms_piece p;
+          p.row0 = I * c->m + off;
+          p.h = (int)std::min ((size_t)MS_SUB, rows - off);
+          p.block = (int)I;
+          p.owner = c->owner_of_block (I);
+          p.lrow0 = (I / (size_t)c->nranks) * c->m + off;
+          c->pieces.push_back (p);
+        }
+    }
+  c->block_first_piece[c->nblocks] = c->pieces.size ();
+}
+
+static int
+ctx_free (ms_ctx *c)
+{
+  if (!c)
+    return MS_OK;
+  cudaSetDevice (c->device);
+  cudaDeviceSynchronize ();
+  if (c->nccl)
+    ms_nccl_destroy (c);
+  cudaFree (c->A);
+  cudaFree (c->PB[0]);
+  cudaFree (c->PB[1]);
+  cudaFree (c->Wt);
+  for (int i = 0; i < 5; i++)
+    cudaFree (c->vec[i]);
+  cudaFree (c->acc);
+  cudaFree (c->scratch);
+  cudaFree (c->flags);
+  cudaFree (c->d_stage);
+  if (c->h_flags)
+    cudaFreeHost (c->h_flags);
+  if (c->h_pinned)
+    cudaFreeHost (c->h_pinned);
+  for (auto e : c->ev_pool)
+    cudaEventDestroy (e);
+  if (c->ev_t0)
+    cudaEventDestroy (c->ev_t0);
+  if (c->ev_t1)
+    cudaEventDestroy (c->ev_t1);
+  if (c->s_main)
+    cudaStreamDestroy (c->s_main);
+  if (c->s_panel)
+    cudaStreamDestroy (c->s_panel);
+  cudaGetLastError ();
+  delete c;
+  return MS_OK;
+}
+
+extern "C" int
+ms_get_unique_id (void *id128)
+{
+  MS_CHECK_ARG (id128 != nullptr, "id buffer is null");
+  return ms_nccl_unique_id (id128);
+}
+
+extern "C" int
+ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, const void *unique_id)
+{
+  MS_CHECK_ARG (out != nullptr, "out is null");
+  *out = nullptr;
+  MS_CHECK_ARG (n >= 1 && m >= 1, "n and m must be positive");
+  MS_CHECK_ARG (nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+  MS_CHECK_ARG (nranks == 1 || unique_id != nullptr, "unique_id required when nranks > 1");
+  MS_CHECK_ARG (n < ((size_t)1 << 31), "n too large");
+  MS_TRY (require_device (device));
+
+  ms_ctx *c = new ms_ctx ();
+  c->n = n;
+  c->m = m;
+  c->device = device;
+  c->rank = rank;
+  c->nranks = nranks;
+  c->nblocks = n / m + (n % m > 0);
+  c->ld = round_up (n, MS_CHUNK);
+  c->hpb = round_up (m, MS_SUB);
+  c->fast = (m % MS_SUB == 0);
+  c->rows_local = 0;
+  for (size_t I = rank; I < c->nblocks; I += (size_t)nranks)
+    c->rows_local += c->block_rows (I);
+  c->rows_alloc = round_up (std::max (c->rows_local, (size_t)1), MS_BM);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties (&prop, device);
+  c->sm_count = prop.multiProcessorCount;
+  build_pieces (c);
+
+  auto fail = [&] (int code) {
+    ctx_free (c);
+    return code;
+  };
+#define CK(expr)                                                                       \
+  do                                                                                   \
+    {                                                                                  \
+      cudaError_t e__ = (expr);                                                        \
+      if (e__ != cudaSuccess)                                                          \
+        {                                                                              \
+          ms_set_error ("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                  \
+                        cudaGetErrorString (e__));                                     \
+          return fail (MS_ERR_CUDA);                                                   \
+        }                                                                              \
+    }                                                                                  \
+  while (0)
+
+  size_t a_bytes = c->rows_alloc * c->ld * sizeof (double);
+  size_t pb_bytes = c->ld * c->hpb * sizeof (double);
+  CK (cudaMalloc (&c->A, a_bytes));
+  CK (cudaMemset (c->A, 0, a_bytes));
+  for (int b = 0; b < 2; b++)
+    {
+      CK (cudaMalloc (&c->PB[b], pb_bytes));
+      CK (cudaMemset (c->PB[b], 0, pb_bytes));
+    }
+  CK (cudaMalloc (&c->Wt, MS_SUB * MS_SUB * sizeof (double)));
+  CK (cudaMemset (c->Wt, 0, MS_SUB * MS_SUB * sizeof (double)));
+  for (int i = 0; i < 5; i++)
+    {
+      CK (cudaMalloc (&c->vec[i], (c->ld + MS_SUB) * sizeof (double)));
+      CK (cudaMemset (c->vec[i], 0, (c->ld + MS_SUB) * sizeof (double)));
+    }
+  CK (cudaMalloc (&c->acc, (c->ld + MS_SUB) * sizeof (double)));
+  CK (cudaMalloc (&c->flags, 8 * sizeof (int)));
+  CK (cudaMemset (c->flags, 0, 8 * sizeof (int)));
+  CK (cudaHostAlloc (&c->h_flags, 8 * sizeof (int), cudaHostAllocDefault));
+  c->stage_doubles = MS_STAGE_DOUBLES;
+  CK (cudaMalloc (&c->d_stage, 2 * c->stage_doubles * sizeof (double)));
+  CK (cudaHostAlloc (&c->h_pinned, 2 * c->stage_doubles * sizeof (double), cudaHostAllocDefault));
+
+  int lo = 0, hi = 0;
+  CK (cudaDeviceGetStreamPriorityRange (&lo, &hi));
+  CK (cudaStreamCreateWithPriority (&c->s_main, cudaStreamNonBlocking, lo));
+  CK (cudaStreamCreateWithPriority (&c->s_panel, cudaStreamNonBlocking, hi));
+  CK (cudaEventCreate (&c->ev_t0));
+  CK (cudaEventCreate (&c->ev_t1));
+  c->ev_pool.resize (2 * c->nblocks + 2);
+  for (auto &e : c->ev_pool)
+    CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+#undef CK
+  int r = ms_tile_setup (c);
+  if (r < 0)
+    return fail (r);
+  if (nranks > 1)
+    {
+      r = ms_nccl_init (c, unique_id);
+      if (r < 0)
+        return fail (r);
+    }
+  const char *e = getenv ("MS_FORCE_GENERIC");
+  if (e && atoi (e))
+    c->force_generic = true;
+  e = getenv ("MS_NO_LOOKAHEAD");
+  if (e && atoi (e))
+    c->lookahead = false;
+  *out = c;
+  return MS_OK;
+}
+
+extern "C" int
+ms_destroy (ms_ctx *ctx)
+{
+  return ctx_free (ctx);
+}
+
+extern "C" int
+ms_set_option (ms_ctx *c, const char *key, long value)
+{
+  MS_CHECK_ARG (c && key, "null argument");
+  if (!strcmp (key, "force_generic"))
+    c->force_generic = value != 0;
+  else if (!strcmp (key, "lookahead"))
+    c->lookahead = value != 0;
+  else if (!strcmp (key, "profile_update"))
+    c->profile_update = value != 0;
+  else
+    {
+      ms_set_error ("unknown option %s", key);
+      return MS_ERR_ARG;
+    }
+  return MS_OK;
+}
+
+extern "C" int
+ms_get_stats (ms_ctx *c, ms_stats *out)
+{
+  MS_CHECK_ARG (c && out, "null argument");
+  *out = c->stats;
+  return MS_OK;
+}
+
+extern "C" int
+ms_sync (ms_ctx *c)
+{
+  MS_CHECK_ARG (c, "null ctx");
+  MS_CUDA (cudaSetDevice (c->device));
+  MS_CUDA (cudaStreamSynchronize (c->s_panel));
+  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  return MS_OK;
+}
+
+struct phase_timer
+{
+  ms_ctx *c;
+  double *slot;
+  phase_timer (ms_ctx *c_, double *slot_) : c (c_), slot (slot_) { cudaEventRecord (c->ev_t0, c->s_main); }
+  int finish ()
+  {
+    MS_CUDA (cudaEventRecord (c->ev_t1, c->s_main));
+    MS_CUDA (cudaEventSynchronize (c->ev_t1));
+    float ms = 0;
+    MS_CUDA (cudaEventElapsedTime (&ms, c->ev_t0, c->ev_t1));
+    *slot = ms;
+    return MS_OK;
+  }
+};
+
+// ----------------------------------------------------------------------------- init
+extern "C" int
+ms_init_formula (ms_ctx *c, int kind)
+{
+  MS_CHECK_ARG (c, "null ctx");
+  MS_CHECK_ARG (kind == MS_FORMULA_F1 || kind == MS_FORMULA_HILBERT, "unknown formula");
+  MS_CUDA (cudaSetDevice (c->device));
+  phase_timer t (c, &c->stats.init_ms);
+  MS_TRY (ms_k_fill_formula (c, kind, c->s_main));
+  return t.finish ();
+}
+
+static bool
+is_pinned_host (const void *p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes (&a, p) != cudaSuccess)
+    {
+      cudaGetLastError ();
+      return false;
+    }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// host -> device copy of `cnt` doubles into d_stage half `half`; pageable sources go through the
+// pinned staging buffer ("staged once through pinned memory").
+static int
+stage_h2d (ms_ctx *c, int half, const double *src, size_t cnt)
+{
+  double *dst = c->d_stage + (size_t)half * c->stage_doubles;
+  const double *from = src;
+  if (!is_pinned_host (src))
+    {
+      double *pin = c->h_pinned + (size_t)half * c->stage_doubles;
+      memcpy (pin, src, cnt * sizeof (double));
+      from = pin;
+    }
+  MS_CUDA (cudaMemcpyAsync (dst, from, cnt * sizeof (double), cudaMemcpyHostToDevice, c->s_main));
+  c->stats.h2d_bytes += (long long)(cnt * sizeof (double));
+  return MS_OK;
+}
+
+extern "C" int
+ms_upload_rows (ms_ctx *c, const double *rows, size_t row0, size_t nrows, size_t ld_host)
+{
+  MS_CHECK_ARG (c && rows, "null argument");
+  MS_CHECK_ARG (row0 + nrows <= c->n && ld_host >= c->n, "row range / ld out of bounds");
+  MS_CUDA (cudaSetDevice (c->device));
+  size_t per = std::max ((size_t)1, c->stage_doubles / ld_host);
+  MS_CHECK_ARG (ld_host <= c->stage_doubles, "row longer than the staging buffer");
+  int half = 0;
+  for (size_t r = 0; r < nrows; r += per)
+    {
+      size_t cnt = std::min (per, nrows - r);
+      // the half is free once the unpack kernel that read it (two iterations ago) has run:
+      // both are on s_main, so stream order already guarantees it for the device side; the
+      // pinned half is reused only after the copy that read it completed:
+      if (!is_pinned_host (rows))
+        MS_CUDA (cudaStreamSynchronize (c->s_main));
+      MS_TRY (stage_h2d (c, half, rows + r * ld_host, cnt * ld_host));
+      MS_TRY (ms_k_unpack_rows (c, c->d_stage + (size_t)half * c->stage_doubles, row0 + r, cnt, ld_host,
+                                c->s_main));
+      half ^= 1;
+    }
+  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  return MS_OK;
+}
+
+// Walk the reference's packed body block column by block column, in row ranges that fit the
+// staging buffer.  Row i of block column J (width w) starts at packed offset:
+//   i < J*m : base_J + i*w ;  else base_J + J*m*w + ii*w - ii(ii-1)/2  (ii = i - J*m; row ii has
+//   w - ii entries), base_J = sum_{K<J} (K*m*m + m(m+1)/2)        (src/init.cpp:29-58)
+static int
+packed_transfer (ms_ctx *c, double *body, int to_packed)
+{
+  MS_CUDA (cudaSetDevice (c->device));
+  const size_t n = c->n, m = c->m;
+  size_t base = 0;
+  bool pinned = is_pinned_host (body);
+  int half = 0;
+  for (size_t J = 0; J < c->nblocks; J++)
+    {
+      size_t w = c->block_rows (J);  // column width == height of block row J
+      size_t rows_total = J * m + w;
+      auto row_off = [&] (size_t i) -> size_t {
+        if (i <= J * m)
+          return i * w;
+        size_t ii = i - J * m;
+        return J * m * w + ii * w - (ii * (ii - 1)) / 2;
+      };
+      size_t i0 = 0;
+      while (i0 < rows_total)
+        {
+          size_t i1 = i0;
+          while (i1 < rows_total && row_off (i1 + 1) - row_off (i0) <= c->stage_doubles)
+            i1++;
+          MS_CHECK_ARG (i1 > i0, "one row of a block column exceeds the staging buffer");
+          size_t seg_base = row_off (i0);
+          size_t cnt = row_off (i1) - seg_base;
+          double *dseg = c->d_stage + (size_t)half * c->stage_doubles;
+          double *hseg = body + base + seg_base;
+          if (!to_packed)
+            {
+              if (!pinned)
+                MS_CUDA (cudaStreamSynchronize (c->s_main));
+              MS_TRY (stage_h2d (c, half, hseg, cnt));
+              MS_TRY (ms_k_packed_rows (c, dseg, J, w, i0, i1, seg_base, 0, c->s_main));
+            }
+          else
+            {
+              MS_TRY (ms_k_packed_rows (c, dseg, J, w, i0, i1, seg_base, 1, c->s_main));
+              if (pinned)
+                MS_CUDA (cudaMemcpyAsync (hseg, dseg, cnt * sizeof (double), cudaMemcpyDeviceToHost, c->s_main));
+              else
+                {
+                  double *pin = c->h_pinned + (size_t)half * c->stage_doubles;
+                  MS_CUDA (cudaMemcpyAsync (pin, dseg, cnt * sizeof (double), cudaMemcpyDeviceToHost, c->s_main));
+                  MS_CUDA (cudaStreamSynchronize (c->s_main));
+                  memcpy (hseg, pin, cnt * sizeof (double));
+                }
+              c->stats.d2h_bytes += (long long)(cnt * sizeof (double));
+            }
+          half ^= 1;
+          i0 = i1;
+        }
+      base += row_off (rows_total);
+    }
+  (void)n;
+  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  return MS_OK;
+}
+
+extern "C" int
+ms_upload_packed (ms_ctx *c, const double *body)
+{
+  MS_CHECK_ARG (c && body, "null argument");
+  MS_CHECK_ARG (c->nranks == 1, "packed transfers use the single-rank reference layout");
+  phase_timer t (c, &c->stats.init_ms);
+  MS_TRY (packed_transfer (c, const_cast<double *> (body), 0));
+  return t.finish ();
+}
+
+extern "C" int
+ms_download_packed (ms_ctx *c, double *body)
+{
+  MS_CHECK_ARG (c && body, "null argument");
+  MS_CHECK_ARG (c->nranks == 1, "packed transfers use the single-rank reference layout");
+  return packed_transfer (c, body, 1);
+}
+
+extern "C" int
+ms_get_row (ms_ctx *c, size_t i, double *buf)
+{
+  MS_CHECK_ARG (c && buf && i < c->n, "bad argument");
+  MS_CUDA (cudaSetDevice (c->device));
+  size_t I = i / c->m;
+  if (c->owner_of_block (I) != c->rank)
+    return MS_OK;  // another rank holds this row (the host mirror asks every rank)
+  MS_CUDA (cudaMemcpyAsync (buf + i, c->row_ptr (i) + i, (c->n - i) * sizeof (double),
+                            cudaMemcpyDeviceToHost, c->s_main));
+  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  c->stats.d2h_bytes += (long long)((c->n - i) * sizeof (double));
+  return MS_OK;
+}
+
+extern "C" int
+ms_get_col (ms_ctx *c, size_t j, double *buf)
+{
+  MS_CHECK_ARG (c && buf && j < c->n, "bad argument");
+  MS_CUDA (cudaSetDevice (c->device));
+  double *tmp = c->d_stage;
+  MS_TRY (ms_k_get_col (c, j, tmp, c->s_main));
+  if (c->nranks > 1)
+    MS_TRY (ms_nccl_allreduce_sum (c, tmp, j + 1, c->s_main));
+  MS_CUDA (cudaMemcpyAsync (buf, tmp, (j + 1) * sizeof (double), cudaMemcpyDeviceToHost, c->s_main));
+  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  c->stats.d2h_bytes += (long long)((j + 1) * sizeof (double));
+  return MS_OK;
+}
+
+extern "C" int
+ms_set_vec (ms_ctx *c, int which, const double *host, size_t count)
+{
+  MS_CHECK_ARG (c && host && which >= 0 && which < 5 && count <= c->n, "bad argument");
+  MS_CUDA (cudaSetDevice (c->device));
+  MS_CUDA (cudaMemcpyAsync (c->vec[which], host, count * sizeof (double), cudaMemcpyHostToDevice, c->s_main));
+  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  c->stats.h2d_bytes += (long long)(count * sizeof (double));
+  return MS_OK;
+}
+
+extern "C" int
+ms_get_vec (ms_ctx *c, int which, double *host, size_t count)
+{
+  MS_CHECK_ARG (c && host && which >= 0 && which < 5 && count <= c->n, "bad argument");
+  MS_CUDA (cudaSetDevice (c->device));
+  MS_CUDA (cudaMemcpyAsync (host, c->vec[which], count * sizeof (double), cudaMemcpyDeviceToHost, c->s_main));
+  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  c->stats.d2h_bytes += (long long)(count * sizeof (double));
+  return MS_OK;
+}
+
+// ----------------------------------------------------------------------------- b and norm
+extern "C" int
+ms_b_and_norm (ms_ctx *c, double *norm)
+{
+  MS_CHECK_ARG (c && norm, "null argument");
+  MS_CUDA (cudaSetDevice (c->device));
+  phase_timer t (c, &c->stats.bnorm_ms);
+  MS_TRY (ms_k_sym_rows (c, MS_SYM_BNORM, nullptr, c->vec[MS_VEC_B], nullptr, c->s_main));
+  double *absp = ms_sym_abs_partial (c);
+  if (c->nranks > 1)
+    {
+      MS_TRY (ms_nccl_allreduce_sum (c, c->vec[MS_VEC_B], c->n, c->s_main));
+      MS_TRY (ms_nccl_allreduce_sum (c, absp, c->n, c->s_main));
+    }
+  double *dmax = absp + c->n;
+  MS_TRY (ms_k_max (c, absp, c->n, dmax, c->s_main));
+  MS_CUDA (cudaMemcpyAsync (norm, dmax, sizeof (double), cudaMemcpyDeviceToHost, c->s_main));
+  MS_TRY (t.finish ());
+  c->stats.d2h_bytes += 8;
+  return MS_OK;
+}
+
+// ----------------------------------------------------------------------------- factor
+static double
+trapezoid_elems (const ms_ctx *c, size_t lrow_begin, size_t lrow_end)
+{
+  // stored elements (j >= i) of local rows [lrow_begin, lrow_end)
+  double total = 0;
+  size_t lr = lrow_begin;
+  while (lr < lrow_end)
+    {
+      size_t lb = lr / c->m;
+      size_t seg_end = std::min ((lb + 1) * c->m, lrow_end);
+      size_t g0 = (lb * (size_t)c->nranks + (size_t)c->rank) * c->m + (lr - lb * c->m);
+      if (g0 < c->n)
+        {
+          double rows = (double)std::min (seg_end - lr, c->n - g0);
+          total += rows * (double)(c->n - g0) - 0.5 * rows * (rows - 1.0);
+        }
+      lr = seg_end;
+    }
+  return total;
+}
+
+static int
+do_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_end, int K, size_t k0,
+           cudaStream_t s, bool count_flops)
+{
+  if (lrow_end <= lrow_begin)
+    return MS_OK;
+  if (count_flops)
+    c->stats.update_flops += 2.0 * K * trapezoid_elems (c, lrow_begin, lrow_end);
+  if (c->fast && !c->force_generic)
+    return ms_k_tile_update (c, pb, I, lrow_begin, lrow_end, K, k0, s);
+  ms_operand P;
+  P.p = c->PB[pb] + k0 * MS_CHUNK;
+  P.ld = 0;
+  P.H = c->hpb;
+  return ms_k_generic_update (c, P, c->vec[MS_VEC_D] + I * c->m + k0, lrow_begin, lrow_end, K, s);
+}
+
+static int
+factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s)
+{
+  const size_t rowsI = c->block_rows (I);
+  const size_t lrowI = (I / (size_t)c->nranks) * c->m;
+  double *diag0 = c->A + lrowI * c->ld + I * c->m;
+  MS_TRY (ms_k_pretest (c, diag0, c->ld, (int)rowsI, thresh, s));
+  for (size_t pi = c->block_first_piece[I]; pi < c->block_first_piece[I + 1]; pi++)
+    {
+      const ms_piece &pc = c->pieces[pi];
+      double *blk = c->A + pc.lrow0 * c->ld + pc.row0;
+      MS_TRY (ms_k_diag (c, blk, c->ld, pc.h, thresh, c->vec[MS_VEC_D] + pc.row0, c->Wt, nullptr, s));
+      size_t col_lo = pc.row0 + (size_t)pc.h;
+      if (col_lo >= c->n)
+        continue;
+      size_t k0 = pc.row0 - I * c->m;
+      if (c->fast && !c->force_generic && pc.h == MS_SUB)
+        MS_TRY (ms_k_tile_panel (c, pb, pc, I, s));
+      else
+        {
+          ms_operand W;
+          W.p = c->Wt;
+          W.ld = 0;
+          W.H = MS_SUB;
+          double *rows = c->A + pc.lrow0 * c->ld;
+          MS_TRY (ms_k_generic_panel (c, W, rows, c->ld, rows, c->ld, pc.h, col_lo, c->PB[pb], c->hpb, k0,
+                                      c->n, s));
+        }
+      // later pieces of the same block row
+      size_t lr_next = pc.lrow0 + (size_t)pc.h;
+      size_t lr_end = lrowI + rowsI;
+      MS_TRY (do_update (c, pb, I, lr_next, lr_end, pc.h, k0, s, false));
+    }
+  return MS_OK;
+}
+
+extern "C" int
+ms_factor (ms_ctx *c, double norma, double *elapsed_s)
+{
+  MS_CHECK_ARG (c, "null ctx");
+  MS_CUDA (cudaSetDevice (c->device));
+  const double thresh = 1.e-14 * norma;  // EPS * norma, src/defines.h:9
+  const size_t nb = c->nblocks;
+  const int P = c->nranks;
+  cudaStream_t sm = c->s_main;
+  cudaStream_t sp = c->lookahead ? c->s_panel : c->s_main;
+  c->stats.update_flops = 0;
+  c->stats.update_launches = 0;
+  c->stats.update_ms = 0;
+  c->stats.used_dmma = 0;
+  MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), sm));
+  std::vector<cudaEvent_t> prof;
+  MS_CUDA (cudaEventRecord (c->ev_t0, sm));
+  cudaEvent_t *ev_panel = c->ev_pool.data ();
+  cudaEvent_t *ev_strip = c->ev_pool.data () + nb + 1;
+  if (c->lookahead)
+    {
+      MS_CUDA (cudaEventRecord (ev_strip[0], sm));
+      MS_CUDA (cudaStreamWaitEvent (sp, ev_strip[0], 0));
+    }
+  for (size_t I = 0; I < nb; I++)
+    {
+      const int pb = (int)(I & 1);
+      const int owner = c->owner_of_block (I);
+      if (c->lookahead && I > 0)
+        MS_CUDA (cudaStreamWaitEvent (sp, ev_strip[I], 0));
+      if (owner == c->rank)
+        MS_TRY (factor_block_row (c, I, pb, thresh, sp));
+      if (P > 1)
+        MS_TRY (ms_nccl_bcast_panel (c, I, pb, owner, sp));
+      if (I + 1 >= nb)
+        {
+          if (c->lookahead)
+            {
+              MS_CUDA (cudaEventRecord (ev_panel[I], sp));
+              MS_CUDA (cudaStreamWaitEvent (sm, ev_panel[I], 0));
+            }
+          break;
+        }
+      if (c->lookahead)
+        {
+          MS_CUDA (cudaEventRecord (ev_panel[I], sp));
+          MS_CUDA (cudaStreamWaitEvent (sm, ev_panel[I], 0));
+        }
+      // local row ranges: block row I+1 (if mine) and everything after it
+      const int K = (int)c->m;  // block row I is full because block row I+1 exists
+      size_t lr_rest;           // first local row of my block rows > I+1
+      if (c->owner_of_block (I + 1) == c->rank)
+        {
+          size_t lr1 = ((I + 1) / (size_t)P) * c->m;
+          size_t lr1_end = lr1 + c->block_rows (I + 1);
+          auto run = [&] () { return do_update (c, pb, I, lr1, lr1_end, K, 0, sm, true); };
+          if (c->profile_update)
+            {
+              cudaEvent_t a, b;
+              MS_CUDA (cudaEventCreate (&a));
+              MS_CUDA (cudaEventCreate (&b));
+              MS_CUDA (cudaEventRecord (a, sm));
+              MS_TRY (run ());
+              MS_CUDA (cudaEventRecord (b, sm));
+              prof.push_back (a);
+              prof.push_back (b);
+            }
+          else
+            MS_TRY (run ());
+          lr_rest = lr1_end;
+        }
+      else
+        {
+          // my first block row with global index > I+1
+          size_t Jn = I + 2;
+          while (Jn < nb && c->owner_of_block (Jn) != c->rank)
+            Jn++;
+          lr_rest = Jn < nb ? (Jn / (size_t)P) * c->m : c->rows_local;
+        }
+      if (c->lookahead)
+        MS_CUDA (cudaEventRecord (ev_strip[I + 1], sm));
+      if (lr_rest < c->rows_local)
+        {
+          auto run = [&] () { return do_update (c, pb, I, lr_rest, c->rows_local, K, 0, sm, true); };
+          if (c->profile_update)
+            {
+              cudaEvent_t a, b;
+              MS_CUDA (cudaEventCreate (&a));
+              MS_CUDA (cudaEventCreate (&b));
+              MS_CUDA (cudaEventRecord (a, sm));
+              MS_TRY (run ());
+              MS_CUDA (cudaEventRecord (b, sm));
+              prof.push_back (a);
+              prof.push_back (b);
+            }
+          else
+            MS_TRY (run ());
+        }
+    }
+  MS_CUDA (cudaMemcpyAsync (c->h_flags, c->flags, 8 * sizeof (int), cudaMemcpyDeviceToHost, sm));
+  MS_CUDA (cudaEventRecord (c->ev_t1, sm));
+  MS_CUDA (cudaEventSynchronize (c->ev_t1));
+  MS_CUDA (cudaStreamSynchronize (c->s_panel));
+  float ms = 0;
+  MS_CUDA (cudaEventElapsedTime (&ms, c->ev_t0, c->ev_t1));
+  c->stats.factor_ms = ms;
+  if (elapsed_s)
+    *elapsed_s = ms * 1e-3;
+  for (size_t i = 0; i + 1 < prof.size (); i += 2)
+    {
+      float t = 0;
+      MS_CUDA (cudaEventElapsedTime (&t, prof[i], prof[i + 1]));
+      c->stats.update_ms += t;
+    }
+  for (auto e : prof)
+    cudaEventDestroy (e);
+  int failed = c->h_flags[0] != 0;
+  if (P > 1)
+    MS_TRY (ms_nccl_agree_flag (c, &failed));
+  return failed ? MS_NUMERICAL_FAILURE : MS_OK;
+}
+
+// ----------------------------------------------------------------------------- solves
+extern "C" int
+ms_solve_forward (ms_ctx *c, double norma)
+{
+  MS_CHECK_ARG (c, "null ctx");
+  MS_CUDA (cudaSetDevice (c->device));
+  const double thresh = 1.e-14 * norma;
+  cudaStream_t s = c->s_main;
+  phase_timer t (c, &c->stats.forward_ms);
+  MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), s));
+  MS_CUDA (cudaMemsetAsync (c->acc, 0, (c->ld + MS_SUB) * sizeof (double), s));
+  if (c->nranks > 1)
+    MS_CUDA (cudaMemsetAsync (c->vec[MS_VEC_Y], 0, c->ld * sizeof (double), s));
+  for (size_t I = 0; I < c->nblocks; I++)
+    {
+      int owner = c->owner_of_block (I);
+      if (c->nranks > 1)
+        MS_TRY (ms_nccl_reduce_sum (c, c->acc + I * c->m, c->block_rows (I), owner, s));
+      if (owner != c->rank)
+        continue;
+      for (size_t pi = c->block_first_piece[I]; pi < c->block_first_piece[I + 1]; pi++)
+        MS_TRY (ms_k_forward_step (c, c->pieces[pi], thresh, s));
+    }
+  if (c->nranks > 1)
+    MS_TRY (ms_nccl_allreduce_sum (c, c->vec[MS_VEC_Y], c->n, s));
+  MS_CUDA (cudaMemcpyAsync (c->h_flags, c->flags, 8 * sizeof (int), cudaMemcpyDeviceToHost, s));
+  MS_TRY (t.finish ());
+  int failed = c->h_flags[0] != 0;
+  if (c->nranks > 1)
+    MS_TRY (ms_nccl_agree_flag (c, &failed));
+  return failed ? MS_NUMERICAL_FAILURE : MS_OK;
+}
+
+extern "C" int
+ms_solve_backward (ms_ctx *c, double norma)
+{
+  MS_CHECK_ARG (c, "null ctx");
+  MS_CUDA (cudaSetDevice (c->device));
+  const double thresh = 1.e-14 * norma;
+  cudaStream_t s = c->s_main;
+  phase_timer t (c, &c->stats.backward_ms);
+  MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), s));
+  MS_CUDA (cudaMemsetAsync (c->acc, 0, (c->ld + MS_SUB) * sizeof (double), s));
+  for (size_t I = c->nblocks; I-- > 0;)
+    {
+      int owner = c->owner_of_block (I);
+      // local rows strictly above block row I on this rank
+      size_t blocks_before = I / (size_t)c->nranks + ((I % (size_t)c->nranks) > (size_t)c->rank ? 1 : 0);
+      size_t lrows_before_block = blocks_before * c->m;
+      if (owner == c->rank)
+        {
+          for (size_t pi = c->block_first_piece[I + 1]; pi-- > c->block_first_piece[I];)
+            {
+              const ms_piece &pc = c->pieces[pi];
+              MS_TRY (ms_k_backward_step (c, pc, pc.lrow0, thresh, s));
+            }
+        }
+      if (c->nranks > 1)
+        {
+          MS_TRY (ms_nccl_bcast (c, c->vec[MS_VEC_X] + I * c->m, c->block_rows (I), owner, s));
+          if (owner != c->rank)
+            for (size_t pi = c->block_first_piece[I + 1]; pi-- > c->block_first_piece[I];)
+              MS_TRY (ms_k_backward_step (c, c->pieces[pi], lrows_before_block, thresh, s));
+        }
+    }
+  MS_CUDA (cudaMemcpyAsync (c->h_flags, c->flags, 8 * sizeof (int), cudaMemcpyDeviceToHost, s));
+  MS_TRY (t.finish ());
+  int failed = c->h_flags[0] != 0;
+  if (c->nranks > 1)
+    MS_TRY (ms_nccl_agree_flag (c, &failed));
+  return failed ? MS_NUMERICAL_FAILURE : MS_OK;
+}
+
+// ----------------------------------------------------------------------------- residual
+extern "C" int
+ms_residual (ms_ctx *c, double *resid2, double *err2)
+{
+  MS_CHECK_ARG (c && resid2 && err2, "null argument");
+  MS_CUDA (cudaSetDevice (c->device));
+  cudaStream_t s = c->s_main;
+  phase_timer t (c, &c->stats.residual_ms);
+  // r <- A x (symmetric product from the stored triangle), then r -= b inside norms? keep r = Ax - b
+  MS_TRY (ms_k_sym_rows (c, MS_SYM_SYMV, c->vec[MS_VEC_X], c->vec[MS_VEC_R], nullptr, s));
+  if (c->nranks > 1)
+    MS_TRY (ms_nccl_allreduce_sum (c, c->vec[MS_VEC_R], c->n, s));
+  MS_TRY (ms_k_axpy_minus (c, c->vec[MS_VEC_R], c->vec[MS_VEC_B], c->n, s));
+  double *out2 = c->scratch;  // reuse: sym_rows scratch is no longer needed
+  MS_TRY (ms_k_norms (c, c->vec[MS_VEC_R], c->vec[MS_VEC_X], c->n, out2, s));
+  double h[2];
+  MS_CUDA (cudaMemcpyAsync (h, out2, 2 * sizeof (double), cudaMemcpyDeviceToHost, s));
+  MS_TRY (t.finish ());
+  *resid2 = sqrt (h[0]);
+  *err2 = sqrt (h[1]);
+  c->stats.d2h_bytes += 16;
+  return MS_OK;
+}
+
+// ----------------------------------------------------------------------------- block API
+// Stateless entry points working on host buffers; a small private context supplies the stream,
+// the flag word and scratch memory.
+static ms_ctx *g_blk = nullptr;
+static std::mutex g_blk_mu;
+
+static int
+blk_ctx (ms_ctx **out)
+{
+  std::lock_guard<std::mutex> lk (g_blk_mu);
+  if (!g_blk)
+    {
+      int dev = 0;
+      const char *e = getenv ("MS_DEVICE");
+      if (e)
+        dev = atoi (e);
+      int r = ms_create (&g_blk, 64, 64, dev, 0, 1, nullptr);
+      if (r < 0)
+        return r;
+    }
+  MS_CUDA (cudaSetDevice (g_blk->device));
+  *out = g_blk;
+  return MS_OK;
+}
+
+struct dev_buf
+{
+  double *p = nullptr;
+  ~dev_buf () { cudaFree (p); }
+  int alloc (size_t cnt) { MS_CUDA (cudaMalloc (&p, std::max (cnt, (size_t)1) * sizeof (double))); return MS_OK; }
+};
+
+static void
+unpack_upper (const double *packed, double *full, int w)
+{
+  size_t pos = 0;
+  for (int i = 0; i < w; i++)
+    for (int j = 0; j < w; j++)
+      full[(size_t)i * w + j] = j >= i ? packed[pos++] : 0.0;
+}
+
+static void
+pack_upper (const double *full, double *packed, int w)
+{
+  size_t pos = 0;
+  for (int i = 0; i < w; i++)
+    for (int j = i; j < w; j++)
+      packed[pos++] = full[(size_t)i * w + j];
+}
+
+static int
+blk_flag (ms_ctx *c, int *flag)
+{
+  MS_CUDA (cudaMemcpyAsync (c->h_flags, c->flags, sizeof (int), cudaMemcpyDeviceToHost, c->s_main));
+  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  *flag = c->h_flags[0] != 0;
+  return MS_OK;
+}
+
+extern "C" int
+ms_block_diag_factor (double *a_packed, double *d, int w, double norma)
+{
+  MS_CHECK_ARG (a_packed && d && w >= 1 && w <= 112, "bad argument (1 <= w <= 112)");
+  ms_ctx *c;
+  MS_TRY (blk_ctx (&c));
+  std::vector<double> full ((size_t)w * w);
+  unpack_upper (a_packed, full.data (), w);
+  dev_buf da, dd;
+  MS_TRY (da.alloc ((size_t)w * w));
+  MS_TRY (dd.alloc (w));
+  cudaStream_t s = c->s_main;
+  MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), s));
+  MS_CUDA (cudaMemcpyAsync (da.p, full.data (), full.size () * 8, cudaMemcpyHostToDevice, s));
+  MS_TRY (ms_k_pretest (c, da.p, w, w, 1.e-14 * norma, s));
+  MS_TRY (ms_k_diag (c, da.p, w, w, 1.e-14 * norma, dd.p, nullptr, nullptr, s));
+  MS_CUDA (cudaMemcpyAsync (full.data (), da.p, full.size () * 8, cudaMemcpyDeviceToHost, s));
+  MS_CUDA (cudaMemcpyAsync (d, dd.p, w * 8, cudaMemcpyDeviceToHost, s));
+  int flag;
+  MS_TRY (blk_flag (c, &flag));
+  pack_upper (full.data (), a_packed, w);
+  return flag ? MS_NUMERICAL_FAILURE : MS_OK;
+}
+
+// The inverse is produced by the same kernel that factors; to invert a GIVEN factor R we hand it
+// R^T R's ... no: we run only the K2 half by factoring nothing.  The diag kernel's inverse stage
+// reads the factored block from shared memory, so we feed it A := R^T R?  That would change the
+// rounding.  Instead a dedicated thin kernel below reuses the same column sweep.
+__global__ void __launch_bounds__ (256)
+upper_inverse_kernel (const double *__restrict__ a, int w, double thresh, double *__restrict__ inv, int *flags)
+{
+  extern __shared__ double sm[];
+  const int S = w + 1;
+  double *r = sm, *v = sm + (size_t)w * S;
+  for (int e = threadIdx.x; e < w * w; e += 256)
+    {
+      int i = e / w, j = e - i * w;
+      r[i * S + j] = a[(size_t)i * w + j];
+      v[i * S + j] = 0.0;
+    }
+  __syncthreads ();
+  for (int i = threadIdx.x; i < w; i += 256)
+    if (fabs (r[i * S + i]) < thresh)
+      flags[0] = 1;
+  for (int j = threadIdx.x; j < w; j += 256)
+    for (int i = j; i >= 0; i--)
+      {
+        double val;
+        if (i == j)
+          val = __ddiv_rn (1.0, r[i * S + i]);
+        else
+          {
+            double sum = 0;
+            for (int k = i + 1; k <= j; k++)
+              sum = __dadd_rn (sum, __dmul_rn (r[i * S + k], v[k * S + j]));
+            val = __ddiv_rn (-sum, r[i * S + i]);
+          }
+        v[i * S + j] = val;
+      }
+  __syncthreads ();
+  for (int e = threadIdx.x; e < w * w; e += 256)
+    {
+      int i = e / w, j = e - i * w;
+      inv[(size_t)i * w + j] = j >= i ? v[i * S + j] : 0.0;
+    }
+}
+
+extern "C" int
+ms_block_upper_inverse (const double *a_packed, double *inv_packed, int w, double norma)
+{
+  MS_CHECK_ARG (a_packed && inv_packed && w >= 1 && w <= 112, "bad argument (1 <= w <= 112)");
+  ms_ctx *c;
+  MS_TRY (blk_ctx (&c));
+  std::vector<double> full ((size_t)w * w);
+  unpack_upper (a_packed, full.data (), w);
+  dev_buf da, di;
+  MS_TRY (da.alloc ((size_t)w * w));
+  MS_TRY (di.alloc ((size_t)w * w));
+  cudaStream_t s = c->s_main;
+  MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), s));
+  MS_CUDA (cudaMemcpyAsync (da.p, full.data (), full.size () * 8, cudaMemcpyHostToDevice, s));
+  size_t smem = 2 * (size_t)w * (w + 1) * sizeof (double);
+  MS_CUDA (cudaFuncSetAttribute (upper_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  upper_inverse_kernel<<<1, 256, smem, s>>> (da.p, w, 1.e-14 * norma, di.p, c->flags);
+  c->stats.kernel_launches++;
+  MS_CUDA (cudaGetLastError ());
+  MS_CUDA (cudaMemcpyAsync (full.data (), di.p, full.size () * 8, cudaMemcpyDeviceToHost, s));
+  int flag;
+  MS_TRY (blk_flag (c, &flag));
+  pack_upper (full.data (), inv_packed, w);
+  return flag ? MS_NUMERICAL_FAILURE : MS_OK;
+}
+
+__global__ void
+scale_cols_to_wt_kernel (const double *__restrict__ inv, const double *__restrict__ D, int h, double *__restrict__ wt)
+{
+  // wt(k, i) = inv(k, i) * D_i, row-major h x h
+  int e = blockIdx.x * 256 + threadIdx.x;
+  if (e < h * h)
+    {
+      int i = e % h;
+      wt[e] = inv[e] * D[i];
+    }
+}
+
+extern "C" int
+ms_block_panel (const double *inv_packed, double *A, const double *D, int h, int w)
+{
+  MS_CHECK_ARG (inv_packed && A && D && h >= 1 && w >= 1, "bad argument");
+  ms_ctx *c;
+  MS_TRY (blk_ctx (&c));
+  std::vector<double> inv ((size_t)h * h);
+  unpack_upper (inv_packed, inv.data (), h);
+  dev_buf dinv, dwt, dsrc, dout, dD;
+  MS_TRY (dinv.alloc ((size_t)h * h));
+  MS_TRY (dwt.alloc ((size_t)h * h));
+  MS_TRY (dsrc.alloc ((size_t)h * w));
+  MS_TRY (dout.alloc ((size_t)h * w));
+  MS_TRY (dD.alloc (h));
+  cudaStream_t s = c->s_main;
+  MS_CUDA (cudaMemcpyAsync (dinv.p, inv.data (), inv.size () * 8, cudaMemcpyHostToDevice, s));
+  MS_CUDA (cudaMemcpyAsync (dsrc.p, A, (size_t)h * w * 8, cudaMemcpyHostToDevice, s));
+  MS_CUDA (cudaMemcpyAsync (dD.p, D, h * 8, cudaMemcpyHostToDevice, s));
+  scale_cols_to_wt_kernel<<<(h * h + 255) / 256, 256, 0, s>>> (dinv.p, dD.p, h, dwt.p);
+  c->stats.kernel_launches++;
+  ms_operand W;
+  W.p = dwt.p;
+  W.ld = (size_t)h;
+  W.H = 0;
+  MS_TRY (ms_k_generic_panel (c, W, dsrc.p, (size_t)w, dout.p, (size_t)w, h, 0, nullptr, 0, 0, (size_t)w, s));
+  MS_CUDA (cudaMemcpyAsync (A, dout.p, (size_t)h * w * 8, cudaMemcpyDeviceToHost, s));
+  MS_CUDA (cudaStreamSynchronize (s));
+  return MS_OK;
+}
+
+static int
+block_update_common (double *A_full, size_t a_cnt, const double *R1, const double *D, const double *R2, int k,
+                     int h, int w, int upper_only)
+{
+  ms_ctx *c;
+  MS_TRY (blk_ctx (&c));
+  dev_buf dA, d1, d2, dD;
+  MS_TRY (dA.alloc (a_cnt));
+  MS_TRY (d1.alloc ((size_t)k * h));
+  MS_TRY (d2.alloc ((size_t)k * w));
+  MS_TRY (dD.alloc (k));
+  cudaStream_t s = c->s_main;
+  MS_CUDA (cudaMemcpyAsync (dA.p, A_full, a_cnt * 8, cudaMemcpyHostToDevice, s));
+  MS_CUDA (cudaMemcpyAsync (d1.p, R1, (size_t)k * h * 8, cudaMemcpyHostToDevice, s));
+  MS_CUDA (cudaMemcpyAsync (d2.p, R2, (size_t)k * w * 8, cudaMemcpyHostToDevice, s));
+  MS_CUDA (cudaMemcpyAsync (dD.p, D, k * 8, cudaMemcpyHostToDevice, s));
+  MS_TRY (ms_k_generic_block_update (c, dA.p, (size_t)w, d1.p, (size_t)h, dD.p, d2.p, (size_t)w, k, h, w,
+                                     upper_only, s));
+  MS_CUDA (cudaMemcpyAsync (A_full, dA.p, a_cnt * 8, cudaMemcpyDeviceToHost, s));
+  MS_CUDA (cudaStreamSynchronize (s));
+  return MS_OK;
+}
+
+extern "C" int
+ms_block_update (double *A, const double *R1, const double *D, const double *R2, int k, int h, int w)
+{
+  MS_CHECK_ARG (A && R1 && D && R2 && k >= 1 && h >= 1 && w >= 1, "bad argument");
+  return block_update_common (A, (size_t)h * w, R1, D, R2, k, h, w, 0);
+}
+
+extern "C" int
+ms_block_update_diag (double *a_packed, const double *R1, const double *D, int k, int w)
+{
+  MS_CHECK_ARG (a_packed && R1 && D && k >= 1 && w >= 1, "bad argument");
+  std::vector<double> full ((size_t)w * w);
+  unpack_upper (a_packed, full.data (), w);
+  MS_TRY (block_update_common (full.data (), full.size (), R1, D, R1, k, w, w, 1));
+  pack_upper (full.data (), a_packed, w);
+  return MS_OK;
+}
+
+static int
+vec_norms (const double *r, const double *x, size_t n, double *out2)
+{
+  ms_ctx *c;
+  MS_TRY (blk_ctx (&c));
+  dev_buf dv, dout;
+  MS_TRY (dv.alloc (n));
+  MS_TRY (dout.alloc (2));
+  cudaStream_t s = c->s_main;
+  MS_CUDA (cudaMemcpyAsync (dv.p, r ? r : x, n * 8, cudaMemcpyHostToDevice, s));
+  MS_TRY (ms_k_norms (c, r ? dv.p : nullptr, x ? dv.p : nullptr, n, dout.p, s));
+  MS_CUDA (cudaMemcpyAsync (out2, dout.p, 16, cudaMemcpyDeviceToHost, s));
+  MS_CUDA (cudaStreamSynchronize (s));
+  return MS_OK;
+}
+
+extern "C" int
+ms_norm2 (const double *v, size_t n, double *out)
+{
+  MS_CHECK_ARG (v && out, "null argument");
+  double o[2];
+  MS_TRY (vec_norms (v, nullptr, n, o));
+  *out = sqrt (o[0]);
+  return MS_OK;
+}
+
+extern "C" int
+ms_error_vs_planted (const double *x, size_t n, double *out)
+{
+  MS_CHECK_ARG (x && out, "null argument");
+  double o[2];
+  MS_TRY (vec_norms (nullptr, x, n, o));
+  *out = sqrt (o[1]);
+  return MS_OK;
+}

@@ -1,0 +1,605 @@
+// ms_kernels_util.cu — HBM-bound helper kernels: formula generator (K8), symmetric
+// row reductions for b / ||A||_inf / residual (K9, K10), layout conversion for host
+// uploads (K11) and the two vector norms.
+//
+// Reference semantics restated by these kernels:
+//   fill_formula   : init_mat + f1 / hilb        src/init.cpp:60-98, test/test_mat.cpp:13-22
+//   sym_rows BNORM : init_b_get_norm             src/init.cpp:492-531
+//   sym_rows SYMV  : find_disrep_vec             src/init.cpp:533-563
+//   norms          : norma_vec2 / find_error     src/matrix_op.cpp:524-548
+//   packed_copy    : the packed block-column layout, src/init.cpp:29-98, defines.h:12-18
+#include "ms_common.cuh"
+
+#define LAUNCH_COUNT(c) ((c)->stats.kernel_launches++)
+
+// global row of local row lr (block-row cyclic: local block b is global block b*P+rank)
+__device__ __forceinline__ size_t
+global_row_of (size_t lr, size_t m, int rank, int nranks)
+{
+  size_t b = lr / m;
+  return (b * (size_t)nranks + (size_t)rank) * m + (lr - b * m);
+}
+
+// ----------------------------------------------------------------------------- K8 generator
+// One CTA row-slab: blockIdx.y walks local rows, blockIdx.x walks 2048-column segments that
+// start at the row's diagonal block.  128-bit stores, 8 bytes written per stored element.
+template <int KIND>
+__global__ void __launch_bounds__ (256)
+fill_formula_kernel (double *__restrict__ A, size_t ld, size_t n, size_t m, size_t rows_local,
+                     int rank, int nranks)
+{
+  for (size_t lr = blockIdx.y; lr < rows_local; lr += gridDim.y)
+    {
+      size_t g = global_row_of (lr, m, rank, nranks);
+      size_t bstart = (g / m) * m;        // first column of the diagonal block
+      size_t j0 = (bstart & ~(size_t)1) + 2 * ((size_t)blockIdx.x * 1024 + threadIdx.x);
+      double *row = A + lr * ld;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        {
+          size_t j = j0 + (size_t)u * 512;
+          if (j >= ld)
+            break;
+          double2 v;
+          double t[2];
+#pragma unroll
+          for (int e = 0; e < 2; e++)
+            {
+              size_t jj = j + e;
+              double val = 0.0;
+              if (jj < n && jj >= bstart)
+                {
+                  size_t hi = jj > g ? jj : g;
+                  if (KIND == MS_FORMULA_F1)
+                    val = (double)(n - hi);                     // n - max(i,j) in integers
+                  else
+                    val = 1. / (double)(g + jj + 1ul);          // hilb
+                }
+              t[e] = val;
+            }
+          v.x = t[0];
+          v.y = t[1];
+          *reinterpret_cast<double2 *> (row + j) = v;
+        }
+    }
+}
+
+int
+ms_k_fill_formula (ms_ctx *c, int kind, cudaStream_t s)
+{
+  if (c->rows_local == 0)
+    return MS_OK;
+  dim3 grid ((unsigned)((c->ld / 2 + 1023) / 1024), (unsigned)(c->rows_local < 16384 ? c->rows_local : 16384));
+  if (kind == MS_FORMULA_F1)
+    fill_formula_kernel<MS_FORMULA_F1><<<grid, 256, 0, s>>> (c->A, c->ld, c->n, c->m, c->rows_local, c->rank, c->nranks);
+  else
+    fill_formula_kernel<MS_FORMULA_HILBERT><<<grid, 256, 0, s>>> (c->A, c->ld, c->n, c->m, c->rows_local, c->rank, c->nranks);
+  LAUNCH_COUNT (c);
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
+// ----------------------------------------------------------------------------- K9 / K10
+// out_i = sum_k w(k) * Asym(i,k) over the full symmetric row, from the stored upper triangle.
+//   BNORM: w(k) = [k even], plus the absolute row sum (for ||A||_inf)
+//   SYMV : w(k) = x_k
+// Pass 1 (row part, k >= i): one CTA per stored row, coalesced, fixed-order tree reduction.
+// Pass 2 (column part, k < i): thread per column walks a chunk of rows; partials per chunk.
+// Pass 3: fixed-order sum of the partials.  No atomics on the values => deterministic.
+__device__ __forceinline__ double
+block_sum_256 (double v, double *sm)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync (0xffffffffu, v, o);
+  __syncthreads ();
+  if ((threadIdx.x & 31) == 0)
+    sm[threadIdx.x >> 5] = v;
+  __syncthreads ();
+  double t = 0;
+  if (threadIdx.x < 32)
+    {
+      t = threadIdx.x < 8 ? sm[threadIdx.x] : 0.0;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1)
+        t += __shfl_xor_sync (0xffffffffu, t, o);
+    }
+  return t;  // valid in thread 0
+}
+
+template <int MODE>
+__global__ void __launch_bounds__ (256)
+sym_rowpart_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m, size_t rows_local,
+                    int rank, int nranks, const double *__restrict__ x, double *__restrict__ rowS,
+                    double *__restrict__ rowA)
+{
+  __shared__ double sm[8];
+  size_t lr = blockIdx.x;
+  size_t g = global_row_of (lr, m, rank, nranks);
+  const double *row = A + lr * ld;
+  double s = 0, sa = 0;
+  for (size_t j = g + threadIdx.x; j < n; j += 256)
+    {
+      double v = row[j];
+      if (MODE == MS_SYM_BNORM)
+        {
+          if ((j & 1) == 0)
+            s += v;
+          sa += fabs (v);
+        }
+      else
+        s += v * x[j];
+    }
+  double ts = block_sum_256 (s, sm);
+  if (threadIdx.x == 0)
+    rowS[g] = ts;
+  if (MODE == MS_SYM_BNORM)
+    {
+      double ta = block_sum_256 (sa, sm);
+      if (threadIdx.x == 0)
+        rowA[g] = ta;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__ (256)
+sym_colpart_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m, size_t rows_local,
+                    int rank, int nranks, size_t rows_per_chunk, const double *__restrict__ x,
+                    double *__restrict__ colS, double *__restrict__ colA)
+{
+  size_t j = (size_t)blockIdx.x * 256 + threadIdx.x;
+  size_t lr0 = (size_t)blockIdx.y * rows_per_chunk;
+  size_t lr1 = lr0 + rows_per_chunk < rows_local ? lr0 + rows_per_chunk : rows_local;
+  double s = 0, sa = 0;
+  if (j < n)
+    {
+      for (size_t lr = lr0; lr < lr1; lr++)
+        {
+          size_t g = global_row_of (lr, m, rank, nranks);
+          if (g >= j)
+            {
+              // rows of later blocks can only be larger; within a block rows ascend
+              if (nranks == 1)
+                break;
+              continue;
+            }
+          double v = A[lr * ld + j];
+          if (MODE == MS_SYM_BNORM)
+            {
+              if ((g & 1) == 0)
+                s += v;
+              sa += fabs (v);
+            }
+          else
+            s += v * x[g];
+        }
+    }
+  if (j < n)
+    {
+      colS[(size_t)blockIdx.y * n + j] = s;
+      if (MODE == MS_SYM_BNORM)
+        colA[(size_t)blockIdx.y * n + j] = sa;
+    }
+}
+
+// total_i = rowS_i + sum_chunks colS[c][i]; BNORM additionally folds the abs sums into a max.
+template <int MODE>
+__global__ void __launch_bounds__ (256)
+sym_finalize_kernel (size_t n, size_t nchunks, const double *__restrict__ rowS,
+                     const double *__restrict__ rowA, const double *__restrict__ colS,
+                     const double *__restrict__ colA, double *__restrict__ out,
+                     double *__restrict__ outA)
+{
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n)
+    return;
+  double s = rowS[i];
+  for (size_t c = 0; c < nchunks; c++)
+    s += colS[c * n + i];
+  out[i] = s;
+  if (MODE == MS_SYM_BNORM)
+    {
+      double a = rowA[i];
+      for (size_t c = 0; c < nchunks; c++)
+        a += colA[c * n + i];
+      outA[i] = a;
+    }
+}
+
+__global__ void __launch_bounds__ (1024)
+max_reduce_kernel (const double *__restrict__ v, size_t n, double *__restrict__ out)
+{
+  __shared__ double sm[32];
+  double best = 0;
+  for (size_t i = threadIdx.x; i < n; i += 1024)
+    best = fmax (best, v[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    best = fmax (best, __shfl_xor_sync (0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0)
+    sm[threadIdx.x >> 5] = best;
+  __syncthreads ();
+  if (threadIdx.x < 32)
+    {
+      best = sm[threadIdx.x];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        best = fmax (best, __shfl_xor_sync (0xffffffffu, best, o));
+      if (threadIdx.x == 0)
+        *out = best;
+    }
+}
+
+// scratch layout (doubles): rowS[n] rowA[n] colS[nchunks*n] colA[nchunks*n] outA[n] max[1]
+int
+ms_k_sym_rows (ms_ctx *c, int mode, const double *xvec, double *out, double *norm_out,
+               cudaStream_t s)
+{
+  size_t n = c->n;
+  size_t rpc = 256;
+  while ((c->rows_local + rpc - 1) / rpc > 64)
+    rpc *= 2;
+  size_t nchunks = c->rows_local ? (c->rows_local + rpc - 1) / rpc : 0;
+  size_t need = 3 * n + 2 * nchunks * n + 16;
+  if (need > c->scratch_doubles)
+    {
+      if (c->scratch)
+        MS_CUDA (cudaFree (c->scratch));
+      c->scratch = nullptr;
+      MS_CUDA (cudaMalloc (&c->scratch, need * sizeof (double)));
+      c->scratch_doubles = need;
+    }
+  double *rowS = c->scratch, *rowA = rowS + n, *colS = rowA + n, *colA = colS + nchunks * n;
+  double *outA = colA + nchunks * n, *mx = outA + n;
+  MS_CUDA (cudaMemsetAsync (rowS, 0, 2 * n * sizeof (double), s));
+  unsigned gx = (unsigned)((n + 255) / 256);
+  if (c->rows_local)
+    {
+      if (mode == MS_SYM_BNORM)
+        {
+          sym_rowpart_kernel<MS_SYM_BNORM><<<(unsigned)c->rows_local, 256, 0, s>>> (
+              c->A, c->ld, n, c->m, c->rows_local, c->rank, c->nranks, xvec, rowS, rowA);
+          sym_colpart_kernel<MS_SYM_BNORM><<<dim3 (gx, (unsigned)nchunks), 256, 0, s>>> (
+              c->A, c->ld, n, c->m, c->rows_local, c->rank, c->nranks, rpc, xvec, colS, colA);
+        }
+      else
+        {
+          sym_rowpart_kernel<MS_SYM_SYMV><<<(unsigned)c->rows_local, 256, 0, s>>> (
+              c->A, c->ld, n, c->m, c->rows_local, c->rank, c->nranks, xvec, rowS, rowA);
+          sym_colpart_kernel<MS_SYM_SYMV><<<dim3 (gx, (unsigned)nchunks), 256, 0, s>>> (
+              c->A, c->ld, n, c->m, c->rows_local, c->rank, c->nranks, rpc, xvec, colS, colA);
+        }
+      c->stats.kernel_launches += 2;
+    }
+  if (mode == MS_SYM_BNORM)
+    sym_finalize_kernel<MS_SYM_BNORM><<<gx, 256, 0, s>>> (n, nchunks, rowS, rowA, colS, colA, out, outA);
+  else
+    sym_finalize_kernel<MS_SYM_SYMV><<<gx, 256, 0, s>>> (n, nchunks, rowS, rowA, colS, colA, out, outA);
+  LAUNCH_COUNT (c);
+  if (mode == MS_SYM_BNORM && norm_out)
+    {
+      // outA holds this rank's partial abs row sums; the caller all-reduces them when
+      // nranks > 1 and then takes the max via ms_k_max (norm_out == device pointer).
+      (void)mx;
+    }
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
+int
+ms_k_max (ms_ctx *c, const double *v, size_t n, double *d_out, cudaStream_t s)
+{
+  max_reduce_kernel<<<1, 1024, 0, s>>> (v, n, d_out);
+  LAUNCH_COUNT (c);
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
+double *
+ms_sym_abs_partial (ms_ctx *c)
+{
+  // location of outA inside the scratch area of the last ms_k_sym_rows call
+  size_t n = c->n;
+  size_t rpc = 256;
+  while ((c->rows_local + rpc - 1) / rpc > 64)
+    rpc *= 2;
+  size_t nchunks = c->rows_local ? (c->rows_local + rpc - 1) / rpc : 0;
+  return c->scratch + 2 * n + 2 * nchunks * n;
+}
+
+// ----------------------------------------------------------------------------- norms
+// out[0] = sum r_i^2, out[1] = sum (x_i - [i even])^2   (square roots taken by the caller)
+__global__ void __launch_bounds__ (1024)
+norms_kernel (const double *__restrict__ r, const double *__restrict__ x, size_t n,
+              double *__restrict__ out)
+{
+  __shared__ double sm[2][32];
+  double a = 0, b = 0;
+  for (size_t i = threadIdx.x; i < n; i += 1024)
+    {
+      if (r)
+        a += r[i] * r[i];
+      if (x)
+        {
+          double t = x[i];
+          if ((i & 1) == 0)
+            t -= 1.;
+          b += t * t;
+        }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    {
+      a += __shfl_xor_sync (0xffffffffu, a, o);
+      b += __shfl_xor_sync (0xffffffffu, b, o);
+    }
+  if ((threadIdx.x & 31) == 0)
+    {
+      sm[0][threadIdx.x >> 5] = a;
+      sm[1][threadIdx.x >> 5] = b;
+    }
+  __syncthreads ();
+  if (threadIdx.x < 32)
+    {
+      a = sm[0][threadIdx.x];
+      b = sm[1][threadIdx.x];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        {
+          a += __shfl_xor_sync (0xffffffffu, a, o);
+          b += __shfl_xor_sync (0xffffffffu, b, o);
+        }
+      if (threadIdx.x == 0)
+        {
+          out[0] = a;
+          out[1] = b;
+        }
+    }
+}
+
+int
+ms_k_norms (ms_ctx *c, const double *r, const double *x, size_t n, double *d_out2, cudaStream_t s)
+{
+  norms_kernel<<<1, 1024, 0, s>>> (r, x, n, d_out2);
+  if (c)
+    LAUNCH_COUNT (c);
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
+int
+ms_k_zero (ms_ctx *c, double *p, size_t cnt, cudaStream_t s)
+{
+  (void)c;
+  MS_CUDA (cudaMemsetAsync (p, 0, cnt * sizeof (double), s));
+  return MS_OK;
+}
+
+// ----------------------------------------------------------------------------- K11 uploads
+// d_rows holds nrows full host rows (ld_src apart) starting at global row row0; keep j >= start
+// of the diagonal block for the rows this rank owns.
+__global__ void __launch_bounds__ (256)
+unpack_rows_kernel (double *__restrict__ A, size_t ld, size_t n, size_t m, int rank, int nranks,
+                    const double *__restrict__ src, size_t row0, size_t nrows, size_t ld_src)
+{
+  size_t g = row0 + blockIdx.y;
+  size_t I = g / m;
+  if ((int)(I % (size_t)nranks) != rank)
+    return;
+  size_t lr = (I / (size_t)nranks) * m + (g - I * m);
+  size_t j = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (j < n && j >= I * m)
+    A[lr * ld + j] = src[(size_t)blockIdx.y * ld_src + j];
+}
+
+int
+ms_k_unpack_rows (ms_ctx *c, const double *d_rows, size_t row0, size_t nrows, size_t ld_src,
+                  cudaStream_t s)
+{
+  if (nrows == 0)
+    return MS_OK;
+  dim3 grid ((unsigned)((c->n + 255) / 256), (unsigned)nrows);
+  unpack_rows_kernel<<<grid, 256, 0, s>>> (c->A, c->ld, c->n, c->m, c->rank, c->nranks, d_rows, row0,
+                                          nrows, ld_src);
+  LAUNCH_COUNT (c);
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
+// Rows [i0, i1) of reference block column J (width w, first column J*m) staged at `seg`
+// exactly as they lie in the reference's packed body:
+//   i <  J*m : seg[(i - i0) * w + jj]                       (full rows of the column)
+//   i >= J*m : packed upper triangle, row ii = i - J*m at ii*w - ii(ii-1)/2 ... (defines.h:12-18)
+// `seg_base` is the packed offset of row i0 inside the block column.
+__global__ void __launch_bounds__ (256)
+packed_copy_kernel (double *__restrict__ A, size_t ld, size_t m, int rank, int nranks,
+                    double *__restrict__ seg, size_t J, size_t w, size_t i0, size_t i1,
+                    size_t seg_base, int to_packed)
+{
+  size_t i = i0 + blockIdx.y;
+  if (i >= i1)
+    return;
+  size_t jj = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (jj >= w)
+    return;
+  size_t I = i / m;
+  if ((int)(I % (size_t)nranks) != rank)
+    return;
+  size_t lr = (I / (size_t)nranks) * m + (i - I * m);
+  size_t off;
+  if (i < J * m)
+    off = i * w + jj;
+  else
+    {
+      size_t ii = i - J * m;
+      if (jj < ii)
+        return;
+      off = J * m * w + ii * w + jj - (ii * ii + ii) / 2;
+    }
+  off -= seg_base;
+  double *dev = A + lr * ld + J * m + jj;
+  if (to_packed)
+    seg[off] = *dev;
+  else
+    *dev = seg[off];
+}
+
+int
+ms_k_packed_rows (ms_ctx *c, double *d_seg, size_t J, size_t w, size_t i0, size_t i1,
+                  size_t seg_base, int to_packed, cudaStream_t s)
+{
+  if (i1 <= i0)
+    return MS_OK;
+  dim3 grid ((unsigned)((w + 255) / 256), (unsigned)(i1 - i0));
+  packed_copy_kernel<<<grid, 256, 0, s>>> (c->A, c->ld, c->m, c->rank, c->nranks, d_seg, J, w, i0, i1,
+                                          seg_base, to_packed);
+  LAUNCH_COUNT (c);
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
+// strided column gather for ms_get_col (gather_col, src/init.cpp:446-490)
+__global__ void __launch_bounds__ (256)
+get_col_kernel (const double *__restrict__ A, size_t ld, size_t m, int rank, int nranks, size_t j,
+                double *__restrict__ out)
+{
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i > j)
+    return;
+  size_t I = i / m;
+  double v = 0;
+  if ((int)(I % (size_t)nranks) == rank)
+    v = A[((I / (size_t)nranks) * m + (i - I * m)) * ld + j];
+  out[i] = v;
+}
+
+int
+ms_k_get_col (ms_ctx *c, size_t j, double *d_out, cudaStream_t s)
+{
+  get_col_kernel<<<(unsigned)(j / 256 + 1), 256, 0, s>>> (c->A, c->ld, c->m, c->rank, c->nranks, j, d_out);
+  LAUNCH_COUNT (c);
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
+// ----------------------------------------------------------------------------- probes
+// Register-only DMMA issue loop: the fp64 tensor-pipe ceiling bench.py quotes fractions of.
+__global__ void __launch_bounds__ (256)
+dmma_probe_kernel (double *out, int iters)
+{
+  double c[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; i++)
+    c[i][0] = c[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; it++)
+    {
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        dmma_8x8x4 (c[i][0], c[i][1], a, b);
+    }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++)
+    s += c[i][0] + c[i][1];
+  if (s == 123.456)
+    out[0] = s;
+}
+
+extern "C" int
+ms_probe_dmma_peak (int device, double *tflops)
+{
+  MS_CHECK_ARG (tflops != nullptr, "tflops is null");
+  MS_CUDA (cudaSetDevice (device));
+  cudaDeviceProp prop;
+  MS_CUDA (cudaGetDeviceProperties (&prop, device));
+  double *d;
+  MS_CUDA (cudaMalloc (&d, 64));
+  int iters = 4096;
+  int blocks = prop.multiProcessorCount * 4;
+  cudaEvent_t e0, e1;
+  MS_CUDA (cudaEventCreate (&e0));
+  MS_CUDA (cudaEventCreate (&e1));
+  dmma_probe_kernel<<<blocks, 256>>> (d, 64);
+  MS_CUDA (cudaDeviceSynchronize ());
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++)
+    {
+      MS_CUDA (cudaEventRecord (e0));
+      dmma_probe_kernel<<<blocks, 256>>> (d, iters);
+      MS_CUDA (cudaEventRecord (e1));
+      MS_CUDA (cudaEventSynchronize (e1));
+      float ms;
+      MS_CUDA (cudaEventElapsedTime (&ms, e0, e1));
+      double flops = (double)blocks * 8 /*warps*/ * (double)iters * 16 * 512.0;
+      double tf = flops / (ms * 1e-3) / 1e12;
+      if (tf > best)
+        best = tf;
+    }
+  *tflops = best;
+  cudaEventDestroy (e0);
+  cudaEventDestroy (e1);
+  cudaFree (d);
+  return MS_OK;
+}
+
+__global__ void __launch_bounds__ (256)
+copy_probe_kernel (const double2 *__restrict__ src, double2 *__restrict__ dst, size_t n2)
+{
+  size_t stride = (size_t)gridDim.x * 256;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n2; i += stride)
+    dst[i] = src[i];
+}
+
+extern "C" int
+ms_probe_hbm_copy (int device, size_t bytes, double *gbs)
+{
+  MS_CHECK_ARG (gbs != nullptr, "gbs is null");
+  MS_CUDA (cudaSetDevice (device));
+  cudaDeviceProp prop;
+  MS_CUDA (cudaGetDeviceProperties (&prop, device));
+  double2 *a, *b;
+  size_t n2 = bytes / 16;
+  MS_CUDA (cudaMalloc (&a, n2 * 16));
+  MS_CUDA (cudaMalloc (&b, n2 * 16));
+  MS_CUDA (cudaMemset (a, 0, n2 * 16));
+  cudaEvent_t e0, e1;
+  MS_CUDA (cudaEventCreate (&e0));
+  MS_CUDA (cudaEventCreate (&e1));
+  double best = 0;
+  for (int rep = 0; rep < 6; rep++)
+    {
+      MS_CUDA (cudaEventRecord (e0));
+      copy_probe_kernel<<<prop.multiProcessorCount * 16, 256>>> (a, b, n2);
+      MS_CUDA (cudaEventRecord (e1));
+      MS_CUDA (cudaEventSynchronize (e1));
+      float ms;
+      MS_CUDA (cudaEventElapsedTime (&ms, e0, e1));
+      double g = 2.0 * (double)n2 * 16 / (ms * 1e-3) / 1e9;
+      if (rep > 0 && g > best)
+        best = g;
+    }
+  *gbs = best;
+  cudaEventDestroy (e0);
+  cudaEventDestroy (e1);
+  cudaFree (a);
+  cudaFree (b);
+  return MS_OK;
+}
+
+__global__ void __launch_bounds__ (256)
+axpy_minus_kernel (double *__restrict__ r, const double *__restrict__ b, size_t n)
+{
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n)
+    r[i] -= b[i];
+}
+
+int
+ms_k_axpy_minus (ms_ctx *c, double *r, const double *b, size_t n, cudaStream_t s)
+{
+  axpy_minus_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>> (r, b, n);
+  LAUNCH_COUNT (c);
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
