@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — factor GFLOP/s (n^3/3) + solve time of the blocked R^T D R path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 65536] [--m 256]
+
+N > 1 is launched by torchrun (one rank per GPU; RANK / LOCAL_RANK / WORLD_SIZE from the env).
+Prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json configs[4], the configuration the headline metric is quoted on; it fits
+one 180 GB B200): formula-generated SPD A_ij = n - max(i,j), n = 65536, block size m = 256, fixed
+as N grows ("strong" scaling).  One step = one pass of the hot path with the inputs resident in
+HBM: device generator -> b and ||A||_inf -> factor -> forward sweep -> backward sweep.
+  value        = (n^3/3) / (mean device time of ms_factor, CUDA events on the library's stream,
+                 max over ranks)                                          [GFLOP/s]
+  ms_per_step  = wall time of the whole step between device syncs (max over ranks)
+  e2e          = (n^3/3) / (host-buffer time-to-solution): the step's matrix comes from page-locked
+                 HOST memory through ms_upload_rows, then b/norm, factor, both sweeps and the D2H
+                 read of x and d — all inside the timed region
+  roofline     = the trailing-update tile kernel (K4+K5): algorithmic flops of its launches /
+                 their summed CUDA-event durations, against the fp64 tensor-pipe peak measured in
+                 this run (register-only DMMA.8x8x4 issue loop)
+  cpu_baseline = the UNMODIFIED reference (oracle/_ref/test_mat_ref, its own `elapsed` timer) on
+                 the box's host cores through the minimpi shim, on a bounded sample of the same
+                 workload (smaller n, same generator and m)
+`--impl reference` prints the same line for the reference's CPU path alone.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cholesky_factor_gflops_n3_over_3"
+UNIT = "GFLOP/s"
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.lines = []
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_sample(n, m, cores):
+    """One run of the unmodified reference CLI on `cores` minimpi ranks; returns its `elapsed`."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "test_mat_ref")
+    if not os.path.exists(exe):
+        return None, "oracle/_ref/test_mat_ref not built (needs /root/reference at build time)"
+    env = dict(os.environ, MINIMPI_NP=str(cores))
+    cwd = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(cwd, exist_ok=True)
+    p = subprocess.run([exe, str(n), str(m)], capture_output=True, text=True, env=env, cwd=cwd)
+    mm = re.search(r"residual = (\S+), er = (\S+), elapsed = (\S+) sec", p.stdout)
+    if p.returncode != 0 or not mm:
+        return None, f"reference run failed rc={p.returncode}: {p.stdout[-200:]} {p.stderr[-200:]}"
+    return {"elapsed": float(mm.group(3)), "residual": float(mm.group(1)), "error": float(mm.group(2))}, None
+
+
+def reference_sample_size(n_full):
+    """Bounded sample: same generator and m, n shrunk so one CPU factor takes ~10-30 s."""
+    return min(n_full, int(os.environ.get("MS_BENCH_REF_N", "8192")))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0  # the other ranks of a torchrun launch have nothing to do
+    cores = host_cores()
+    ns = reference_sample_size(args.n)
+    times, last = [], None
+    for it in range(args.warmup + args.steps):
+        r, err = run_reference_sample(ns, args.m, cores)
+        if err:
+            print(json.dumps({"impl": "reference", "unavailable": err}))
+            return 0
+        last = r
+        if it >= args.warmup:
+            times.append(r["elapsed"])
+    t = sum(times) / len(times)
+    gf = ns ** 3 / 3.0 / t / 1e9
+    sample = (f"formula A_ij=n-max(i,j), n={ns}, m={args.m}: reference CPU factor "
+              f"(its own `elapsed` timer), {cores} minimpi ranks on the box's host cores")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gf, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"formula SPD n={args.n} m={args.m}; reference timed on the bounded sample n={ns}",
+                   "n": args.n, "m": args.m, "sample_n": ns},
+        "cpu_baseline": {"value": gf, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": gf, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "residual_abs": last["residual"], "error_abs": last["error"],
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+def our_arm(args):
+    import numpy as np
+    import torch
+    import matrix_solver_b200 as ms
+    from matrix_solver_b200 import dist, layout
+
+    rank, local, world = dist.env_rank()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}"}))
+            return 2
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: bench.py measures the B200 path, there is no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local)
+    dist.init("nccl" if world > 1 else None)
+    n, m = args.n, args.m
+
+    uid = None
+    if world > 1:
+        raw = ms.get_unique_id() if rank == 0 else b""
+        uid = dist.broadcast_bytes(raw, 128)
+    solver = ms.Solver(n, m, device=local, rank=rank, nranks=world, unique_id=uid)
+    solver.set_option("profile_update", 1)
+
+    peak_dmma = ms.probe_dmma_peak(local) if rank == 0 else 0.0
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+
+    def step():
+        solver.init_formula(0)
+        norm = solver.b_and_norm()
+        failed, _ = solver.factor(norm)
+        f2 = solver.solve_forward(norm)
+        f3 = solver.solve_backward(norm)
+        return norm, failed or f2 or f3
+
+    def sync_all():
+        solver.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    st0 = solver.stats()
+    acc = {k: 0.0 for k in ("factor_ms", "forward_ms", "backward_ms", "init_ms", "bnorm_ms", "update_ms",
+                            "update_flops")}
+    any_fail = False
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        norm, failed = step()
+        any_fail |= failed
+        st = solver.stats()
+        for k in acc:
+            acc[k] += st[k]
+    sync_all()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    st1 = solver.stats()
+
+    # correctness evidence of the last step: residual with the regenerated matrix
+    solver.init_formula(0)
+    resid, err = solver.residual()
+    bnorm2 = float(np.linalg.norm(solver.get_vec("b")))
+
+    K = args.steps
+    factor_ms = dist.max_over_ranks(acc["factor_ms"] / K)
+    wall_ms = dist.max_over_ranks(wall / K * 1e3)
+    fwd_ms = dist.max_over_ranks(acc["forward_ms"] / K)
+    bwd_ms = dist.max_over_ranks(acc["backward_ms"] / K)
+    init_ms = dist.max_over_ranks(acc["init_ms"] / K)
+    bnorm_ms = dist.max_over_ranks(acc["bnorm_ms"] / K)
+    upd_ms_rank = acc["update_ms"] / K
+    upd_flops_rank = acc["update_flops"] / K
+    upd_tflops_rank = upd_flops_rank / upd_ms_rank / 1e9 if upd_ms_rank > 0 else 0.0
+    upd_tflops_min = -dist.max_over_ranks(-upd_tflops_rank)
+    launches = dist.sum_over_ranks(st1["kernel_launches"] - st0["kernel_launches"])
+    value = layout.factor_flops(n) / (factor_ms * 1e-3) / 1e9
+
+    # ---- e2e: host buffers in, host results out (rows of A from page-locked memory)
+    e2e = None
+    if not args.no_e2e:
+        rows_mine = layout.rows_local(n, m, rank, world)
+        # every rank keeps the rows it owns, full length, contiguous in block-row order
+        pin = ms.PinnedBuffer(max(rows_mine, 1) * n)
+        blocks = [I for I in range(rank, layout.n_blocks(n, m), world)]
+        solver.init_formula(0)
+        off = 0
+        for I in blocks:
+            h = layout.block_rows(n, m, I)
+            # write block row I so that global column j sits at offset j of each row
+            solver.download_rows_ptr(pin.ptr.value + off * n * 8, I * m, h, n)
+            off += h
+        sync_all()
+        e2e_times = []
+        h2d0, d2h0 = solver.stats()["h2d_bytes"], solver.stats()["d2h_bytes"]
+        for it in range(1 + args.e2e_steps):
+            sync_all()
+            t1 = time.perf_counter()
+            off = 0
+            for I in blocks:
+                h = layout.block_rows(n, m, I)
+                solver.upload_rows_ptr(pin.ptr.value + off * n * 8, I * m, h, n)
+                off += h
+            nrm = solver.b_and_norm()
+            solver.factor(nrm)
+            solver.solve_forward(nrm)
+            solver.solve_backward(nrm)
+            x = solver.get_vec("x")
+            d = solver.get_vec("d")
+            sync_all()
+            if it > 0:
+                e2e_times.append(time.perf_counter() - t1)
+            else:
+                h2d0, d2h0 = solver.stats()["h2d_bytes"], solver.stats()["d2h_bytes"]
+        t_e2e = dist.max_over_ranks(sum(e2e_times) / len(e2e_times))
+        stx = solver.stats()
+        e2e = {"value": layout.factor_flops(n) / t_e2e / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": dist.sum_over_ranks((stx["h2d_bytes"] - h2d0) / len(e2e_times)),
+               "d2h_bytes_per_step": dist.sum_over_ranks((stx["d2h_bytes"] - d2h0) / len(e2e_times)),
+               "seconds": t_e2e, "x_err_vs_planted": float(np.linalg.norm(x - (np.arange(n) % 2 == 0))),
+               "what": "pinned host rows -> ms_upload_rows -> b/norm -> factor -> forward -> backward -> D2H x, d"}
+        pin.free()
+
+    solver.close()
+    if rank != 0:
+        dist.shutdown()
+        return 0
+
+    # ---- cpu baseline (rank 0, N = 1 only): the reference on the host cores, bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = host_cores()
+        ns = reference_sample_size(n)
+        r, errmsg = run_reference_sample(ns, m, cores)
+        if r:
+            cpu = {"value": ns ** 3 / 3.0 / r["elapsed"] / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"formula n={ns}, m={m}: unmodified reference CPU factor, {cores} minimpi ranks, "
+                             f"{r['elapsed']:.2f} s (its own elapsed timer); residual {r['residual']:.3e}"}
+        else:
+            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": errmsg}
+
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "update_kernel_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": wall_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"formula-generated SPD A_ij=n-max(i,j), n={n}, block m={m}, factor+solve "
+                               f"(BASELINE configs[4]); block-row cyclic over {world} GPU(s)",
+                   "n": n, "m": m, "parallelism": f"block-row-cyclic x{world}, NCCL panel broadcast, look-ahead",
+                   "l2": "inputs larger than L2 (matrix %.1f GB per GPU)" % (8.0 * n * n / world / 1e9)},
+        "factor_ms": factor_ms, "forward_ms": fwd_ms, "backward_ms": bwd_ms, "solve_ms": fwd_ms + bwd_ms,
+        "init_ms": init_ms, "bnorm_ms": bnorm_ms,
+        "time_to_solution_ms": init_ms + bnorm_ms + factor_ms + fwd_ms + bwd_ms,
+        "residual_abs": resid, "residual_rel": resid / bnorm2 if bnorm2 else None, "error_abs": err,
+        "numerical_failure": bool(any_fail),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "tile_dmma_kernel<UPDATE> (fp64 DMMA.8x8x4 trailing update)",
+                     "achieved": upd_tflops_min, "peak": peak_dmma, "unit": "TFLOP/s",
+                     "frac": upd_tflops_min / peak_dmma if peak_dmma else None, "traffic": traffic,
+                     "peak_source": "measured in this run: register-only DMMA.8x8x4 issue loop on all SMs "
+                                    "(ms_probe_dmma_peak); MEASURED_PEAKS.json has no fp64 entry; nominal 37 TFLOP/s",
+                     "algorithmic_flops_per_step": dist_safe(upd_flops_rank),
+                     "kernel_ms_per_step": upd_ms_rank,
+                     "whole_factor_frac_of_peak": value / 1e3 / peak_dmma if peak_dmma else None,
+                     "hbm_peak_gbs": peaks.get("hbm_gbs"),
+                     "solve_achieved_gbs": layout.solve_bytes(n) * 2 / ((fwd_ms + bwd_ms) * 1e-3) / 1e9},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    dist.shutdown()
+    return 0
+
+
+def dist_safe(v):
+    return float(v)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("MS_BENCH_N", "65536")))
+    ap.add_argument("--m", type=int, default=int(os.environ.get("MS_BENCH_M", "256")))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return our_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

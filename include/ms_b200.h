@@ -79,15 +79,22 @@ int ms_sync (ms_ctx *ctx);
 int ms_init_formula (ms_ctx *ctx, int kind);
 /* `rows` holds nrows full rows (ld_host doubles apart) starting at global row row0;
  * only j >= i is used, like the reference's file reader.  Rows owned by other ranks are
- * skipped.  Staged through pinned memory. */
+ * skipped.  Page-locked sources are DMA-ed straight into place (one strided copy per block row);
+ * pageable sources are staged through the library's pinned buffer first. */
 int ms_upload_rows (ms_ctx *ctx, const double *rows, size_t row0, size_t nrows,
                     size_t ld_host);
+/* the reverse: the upper part (j >= i, from the start of each row's diagonal block) of the rows
+ * this rank owns inside [row0, row0+nrows) is written into `rows`; other entries are untouched */
+int ms_download_rows (ms_ctx *ctx, double *rows, size_t row0, size_t nrows, size_t ld_host);
+/* page-locked host memory for callers that want the direct-DMA path of the transfers above */
+int ms_host_alloc (void **out, size_t bytes);
+int ms_host_free (void *p);
 /* whole matrix in the reference's single-rank packed block-column layout
- * (src/init.cpp:29-98): n(n+1)/2 doubles.  This is the HOST-buffer entry the e2e
- * benchmark uses. */
+ * (src/init.cpp:29-98): n(n+1)/2 doubles, nranks == 1 only. */
 int ms_upload_packed (ms_ctx *ctx, const double *body);
 int ms_download_packed (ms_ctx *ctx, double *body);
-/* gather_row / gather_col (src/init.cpp:309-490): buf[i..n) resp. buf[0..j] */
+/* gather_row / gather_col (src/init.cpp:309-490): buf[i..n) resp. buf[0..j]; collective when
+ * nranks > 1 (every rank calls, every rank receives) */
 int ms_get_row (ms_ctx *ctx, size_t i, double *buf);
 int ms_get_col (ms_ctx *ctx, size_t j, double *buf);
 

@@ -9,6 +9,7 @@ is visible.
 from .capi import (  # noqa: F401
     MSError,
     NumericalFailure,
+    PinnedBuffer,
     Solver,
     block_diag_factor,
     block_panel,

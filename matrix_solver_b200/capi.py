@@ -58,6 +58,9 @@ def load():
         "ms_sync": (ci, [vp]),
         "ms_init_formula": (ci, [vp, ci]),
         "ms_upload_rows": (ci, [vp, vp, sz, sz, sz]),
+        "ms_download_rows": (ci, [vp, vp, sz, sz, sz]),
+        "ms_host_alloc": (ci, [C.POINTER(vp), sz]),
+        "ms_host_free": (ci, [vp]),
         "ms_upload_packed": (ci, [vp, vp]),
         "ms_download_packed": (ci, [vp, vp]),
         "ms_get_row": (ci, [vp, sz, dp]),
@@ -90,7 +93,7 @@ def load():
 EXPORTED = [
     "ms_last_error", "ms_device_count", "ms_get_unique_id", "ms_create", "ms_destroy",
     "ms_set_option", "ms_get_stats", "ms_sync", "ms_init_formula", "ms_upload_rows",
-    "ms_upload_packed", "ms_download_packed", "ms_get_row", "ms_get_col", "ms_b_and_norm",
+    "ms_download_rows", "ms_host_alloc", "ms_host_free", "ms_upload_packed", "ms_download_packed", "ms_get_row", "ms_get_col", "ms_b_and_norm",
     "ms_factor", "ms_solve_forward", "ms_solve_backward", "ms_residual", "ms_set_vec",
     "ms_get_vec", "ms_block_diag_factor", "ms_block_upper_inverse", "ms_block_panel",
     "ms_block_update", "ms_block_update_diag", "ms_norm2", "ms_error_vs_planted",
@@ -170,6 +173,17 @@ class Solver:
     def upload_rows(self, rows, row0=0):
         rows = np.ascontiguousarray(rows, dtype=np.float64)
         _check(self.L.ms_upload_rows(self.h, rows.ctypes.data, row0, rows.shape[0], rows.shape[1]))
+
+    def upload_rows_ptr(self, ptr, row0, nrows, ld_host):
+        _check(self.L.ms_upload_rows(self.h, ptr, row0, nrows, ld_host))
+
+    def download_rows_ptr(self, ptr, row0, nrows, ld_host):
+        _check(self.L.ms_download_rows(self.h, ptr, row0, nrows, ld_host))
+
+    def download_rows(self, row0, nrows):
+        out = np.zeros((nrows, self.n))
+        _check(self.L.ms_download_rows(self.h, out.ctypes.data, row0, nrows, self.n))
+        return out
 
     def upload_packed(self, body):
         ptr = body if isinstance(body, int) else body.ctypes.data
@@ -291,6 +305,28 @@ def error_vs_planted(x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     _check(load().ms_error_vs_planted(_p(x), len(x), C.byref(out)))
     return out.value
+
+
+class PinnedBuffer:
+    """Page-locked host array of float64 (cudaHostAlloc through the C ABI)."""
+
+    def __init__(self, count):
+        self.count = count
+        self.ptr = C.c_void_p()
+        _check(load().ms_host_alloc(C.byref(self.ptr), count * 8))
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, dp), shape=(count,))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load().ms_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def probe_dmma_peak(device=0):

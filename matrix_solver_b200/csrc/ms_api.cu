@@ -348,29 +348,94 @@ stage_h2d (ms_ctx *c, int half, const double *src, size_t cnt)
   return MS_OK;
 }
 
+// One strided DMA per block row between a page-locked host array of full rows and the device
+// layout: only columns >= the start of the block row's diagonal block move (n(n+m)/2 doubles
+// in total instead of n^2).
+static int
+rows_dma (ms_ctx *c, double *rows, size_t row0, size_t nrows, size_t ld_host, bool to_device)
+{
+  for (size_t I = row0 / c->m; I < c->nblocks && I * c->m < row0 + nrows; I++)
+    {
+      if (c->owner_of_block (I) != c->rank)
+        continue;
+      size_t g0 = std::max (I * c->m, row0);
+      size_t g1 = std::min (I * c->m + c->block_rows (I), row0 + nrows);
+      size_t col0 = I * c->m;
+      double *dev = c->row_ptr (g0) + col0;
+      double *host = rows + (g0 - row0) * ld_host + col0;
+      size_t width = (c->n - col0) * sizeof (double);
+      if (to_device)
+        {
+          MS_CUDA (cudaMemcpy2DAsync (dev, c->ld * 8, host, ld_host * 8, width, g1 - g0, cudaMemcpyHostToDevice, c->s_main));
+          c->stats.h2d_bytes += (long long)(width * (g1 - g0));
+        }
+      else
+        {
+          MS_CUDA (cudaMemcpy2DAsync (host, ld_host * 8, dev, c->ld * 8, width, g1 - g0, cudaMemcpyDeviceToHost, c->s_main));
+          c->stats.d2h_bytes += (long long)(width * (g1 - g0));
+        }
+    }
+  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  return MS_OK;
+}
+
 extern "C" int
 ms_upload_rows (ms_ctx *c, const double *rows, size_t row0, size_t nrows, size_t ld_host)
 {
   MS_CHECK_ARG (c && rows, "null argument");
   MS_CHECK_ARG (row0 + nrows <= c->n && ld_host >= c->n, "row range / ld out of bounds");
   MS_CUDA (cudaSetDevice (c->device));
-  size_t per = std::max ((size_t)1, c->stage_doubles / ld_host);
+  phase_timer t (c, &c->stats.init_ms);
+  if (is_pinned_host (rows))
+    {
+      MS_TRY (rows_dma (c, const_cast<double *> (rows), row0, nrows, ld_host, true));
+      return t.finish ();
+    }
   MS_CHECK_ARG (ld_host <= c->stage_doubles, "row longer than the staging buffer");
+  size_t per = std::max ((size_t)1, c->stage_doubles / ld_host);
   int half = 0;
   for (size_t r = 0; r < nrows; r += per)
     {
       size_t cnt = std::min (per, nrows - r);
-      // the half is free once the unpack kernel that read it (two iterations ago) has run:
-      // both are on s_main, so stream order already guarantees it for the device side; the
-      // pinned half is reused only after the copy that read it completed:
-      if (!is_pinned_host (rows))
-        MS_CUDA (cudaStreamSynchronize (c->s_main));
+      // the pinned half is rewritten by the host: wait until the copy that read it has finished
+      MS_CUDA (cudaStreamSynchronize (c->s_main));
       MS_TRY (stage_h2d (c, half, rows + r * ld_host, cnt * ld_host));
       MS_TRY (ms_k_unpack_rows (c, c->d_stage + (size_t)half * c->stage_doubles, row0 + r, cnt, ld_host,
                                 c->s_main));
       half ^= 1;
     }
-  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  return t.finish ();
+}
+
+extern "C" int
+ms_download_rows (ms_ctx *c, double *rows, size_t row0, size_t nrows, size_t ld_host)
+{
+  MS_CHECK_ARG (c && rows, "null argument");
+  MS_CHECK_ARG (row0 + nrows <= c->n && ld_host >= c->n, "row range / ld out of bounds");
+  MS_CUDA (cudaSetDevice (c->device));
+  return rows_dma (c, rows, row0, nrows, ld_host, false);
+}
+
+extern "C" int
+ms_host_alloc (void **out, size_t bytes)
+{
+  MS_CHECK_ARG (out != nullptr, "out is null");
+  int n = 0;
+  if (cudaGetDeviceCount (&n) != cudaSuccess || n == 0)
+    {
+      cudaGetLastError ();
+      ms_set_error ("no CUDA device visible: this library has no CPU fallback");
+      return MS_ERR_NO_DEVICE;
+    }
+  MS_CUDA (cudaHostAlloc (out, bytes, cudaHostAllocPortable));
+  return MS_OK;
+}
+
+extern "C" int
+ms_host_free (void *p)
+{
+  if (p)
+    MS_CUDA (cudaFreeHost (p));
   return MS_OK;
 }
 
@@ -462,12 +527,24 @@ ms_get_row (ms_ctx *c, size_t i, double *buf)
   MS_CHECK_ARG (c && buf && i < c->n, "bad argument");
   MS_CUDA (cudaSetDevice (c->device));
   size_t I = i / c->m;
-  if (c->owner_of_block (I) != c->rank)
-    return MS_OK;  // another rank holds this row (the host mirror asks every rank)
-  MS_CUDA (cudaMemcpyAsync (buf + i, c->row_ptr (i) + i, (c->n - i) * sizeof (double),
-                            cudaMemcpyDeviceToHost, c->s_main));
+  int owner = c->owner_of_block (I);
+  size_t cnt = c->n - i;
+  const double *src = nullptr;
+  if (c->nranks == 1)
+    src = c->row_ptr (i) + i;
+  else
+    {
+      // collective: the owner's row travels to every rank (the reference gathers it on the root)
+      double *tmp = c->d_stage;
+      if (owner == c->rank)
+        MS_CUDA (cudaMemcpyAsync (tmp, c->row_ptr (i) + i, cnt * sizeof (double), cudaMemcpyDeviceToDevice,
+                                  c->s_main));
+      MS_TRY (ms_nccl_bcast (c, tmp, cnt, owner, c->s_main));
+      src = tmp;
+    }
+  MS_CUDA (cudaMemcpyAsync (buf + i, src, cnt * sizeof (double), cudaMemcpyDeviceToHost, c->s_main));
   MS_CUDA (cudaStreamSynchronize (c->s_main));
-  c->stats.d2h_bytes += (long long)((c->n - i) * sizeof (double));
+  c->stats.d2h_bytes += (long long)(cnt * sizeof (double));
   return MS_OK;
 }
 

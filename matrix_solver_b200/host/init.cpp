@@ -1,0 +1,232 @@
+// init.cpp — host mirror of the reference's src/init.cpp on top of the GPU library.
+//
+//   reference routine (src/init.cpp)          here
+//   compute_alloc_size :4-27                  same count (what this rank WOULD hold on the host)
+//   alloc_rows :29-58                         creates the device-resident problem (ms_create)
+//   init_mat :60-98                           device generator (ms_init_formula) for f1 / hilb,
+//                                             otherwise the callback is evaluated into pinned rows
+//   init_mat_file :100-294                    text parser -> pinned staging -> ms_upload_rows
+//   gather_row / gather_col :309-490          ms_get_row / ms_get_col (one D2H copy)
+//   init_b_get_norm :492-531                  ms_b_and_norm (one pass over the stored triangle)
+//   find_disrep_vec :533-563                  ms_residual
+//   check_res :565-581                        flag consensus already happened inside the library
+#include "init.h"
+
+#include <cstdarg>
+#include <vector>
+
+#include "ms_rt.h"
+
+double
+f1 (size_t i, size_t j, size_t n)
+{
+  return (double)(n - (i > j ? i : j));
+}
+
+double
+hilb (size_t i, size_t j, size_t)
+{
+  return 1. / (double)(i + j + 1ul);
+}
+
+static ms_ctx *
+ctx_of (double **rows_p)
+{
+  ms_ctx *c = ms_rt_ctx (rows_p);
+  if (!c)
+    {
+      fprintf (stderr, "matrix_solver_b200: rows_p was not produced by alloc_rows\n");
+      abort ();
+    }
+  return c;
+}
+
+static void
+must (int rc, const char *what)
+{
+  if (rc < 0)
+    ms_rt_die (what, rc);
+}
+
+size_t
+compute_alloc_size (size_t n, size_t m)
+{
+  const int rank = ms_rt_init (), size = ms_rt_size ();
+  const size_t cols = n / m + (n % m > 0);
+  size_t total = 0;
+  for (size_t J = (size_t)rank; J < cols; J += (size_t)size)
+    {
+      const size_t w = (J + 1) * m <= n ? m : n - J * m;
+      total += J * m * w + w * (w + 1) / 2;
+    }
+  return total;
+}
+
+double *
+alloc_rows (size_t n, size_t m, size_t n_to_alloc, double **rows_p)
+{
+  (void)n_to_alloc;  // the host body is never materialised; the device holds the matrix
+  double *token = nullptr;
+  ms_rt_bind (rows_p, n, m, &token);
+  return token;
+}
+
+// Does f agree with g on a spread of probe points?
+static bool
+same_formula (initializer f, initializer g, size_t n)
+{
+  const size_t probes[] = {0, 1, 2, n / 3, n / 2, n - 1};
+  for (size_t i : probes)
+    for (size_t j : probes)
+      if (i < n && j < n && f (i, j, n) != g (i, j, n))
+        return false;
+  return true;
+}
+
+void
+init_mat (double **rows_p, size_t n, size_t m, initializer f)
+{
+  (void)m;
+  ms_ctx *c = ctx_of (rows_p);
+  if (same_formula (f, f1, n))
+    return must (ms_init_formula (c, MS_FORMULA_F1), "ms_init_formula");
+  if (same_formula (f, hilb, n))
+    return must (ms_init_formula (c, MS_FORMULA_HILBERT), "ms_init_formula");
+  // unknown callback: it is the caller's host code, evaluate it row by row and stage the rows
+  const size_t chunk = std::max<size_t> (1, ((size_t)1 << 21) / n);
+  std::vector<double> rows (chunk * n);
+  for (size_t i0 = 0; i0 < n; i0 += chunk)
+    {
+      const size_t cnt = std::min (chunk, n - i0);
+      for (size_t r = 0; r < cnt; r++)
+        for (size_t j = i0 + r; j < n; j++)
+          rows[r * n + j] = f (i0 + r, j, n);
+      must (ms_upload_rows (c, rows.data (), i0, cnt, n), "ms_upload_rows");
+    }
+}
+
+bool
+init_mat_file (double **rows_p, size_t n, size_t m, const char *filename)
+{
+  (void)m;
+  ms_ctx *c = ctx_of (rows_p);
+  FILE *fd = fopen (filename, "r");
+  if (!fd)
+    {
+      printf ("cant open %s\n", filename);
+      return 0;
+    }
+  const size_t chunk = std::max<size_t> (1, ((size_t)1 << 21) / n);
+  std::vector<double> rows (chunk * n);
+  bool ok = true;
+  for (size_t i0 = 0; i0 < n && ok; i0 += chunk)
+    {
+      size_t cnt = std::min (chunk, n - i0), got = 0;
+      for (; got < cnt && ok; got++)
+        for (size_t j = 0; j < n; j++)
+          if (fscanf (fd, "%lf", &rows[got * n + j]) != 1)
+            {
+              ok = false;
+              break;
+            }
+      if (!ok)
+        got--;  // the row that hit EOF is incomplete
+      if (got > 0)
+        must (ms_upload_rows (c, rows.data (), i0, got, n), "ms_upload_rows");
+    }
+  fclose (fd);
+  if (!ok)
+    printf ("unexpected eof of %s\n", filename);
+  return ok;
+}
+
+bool
+check_args (const int argc, char **argv)
+{
+  return argc > 2 && argc < 5 && atoi (argv[1]) != 0 && atoi (argv[2]) != 0;
+}
+
+void
+gather_row (size_t i, size_t n, size_t m, int root, vec buf, double **rows_p, int action)
+{
+  (void)n;
+  (void)m;
+  (void)root;
+  if (action != 0 || rows_p == nullptr)
+    return;  // the reference frees its static scratch here; nothing to free
+  std::vector<double> tmp;
+  double *dst = buf;
+  if (!dst)  // non-root ranks pass nullptr; the call is still collective
+    {
+      tmp.resize (n);
+      dst = tmp.data ();
+    }
+  must (ms_get_row (ctx_of (rows_p), i, dst), "ms_get_row");
+}
+
+void
+gather_col (size_t j, size_t n, size_t m, int root, vec buf, double **&rows_p)
+{
+  (void)m;
+  (void)root;
+  std::vector<double> tmp;
+  double *dst = buf;
+  if (!dst)
+    {
+      tmp.resize (n);
+      dst = tmp.data ();
+    }
+  must (ms_get_col (ctx_of (rows_p), j, dst), "ms_get_col");
+}
+
+void
+init_b_get_norm (vec b, size_t n, size_t m, int root, double **&rows_p, double &norm)
+{
+  (void)m;
+  (void)root;
+  ms_ctx *c = ctx_of (rows_p);
+  must (ms_b_and_norm (c, &norm), "ms_b_and_norm");
+  if (b)
+    must (ms_get_vec (c, MS_VEC_B, b, n), "ms_get_vec");
+}
+
+void
+find_disrep_vec (vec b, vec x, vec r, size_t n, size_t m, int root, double **&rows_p)
+{
+  (void)m;
+  (void)root;
+  ms_ctx *c = ctx_of (rows_p);
+  // x only exists on the root in the reference; here every rank holds it on its device already,
+  // so host copies are pushed only where the caller has them
+  if (b)
+    must (ms_set_vec (c, MS_VEC_B, b, n), "ms_set_vec");
+  if (x)
+    must (ms_set_vec (c, MS_VEC_X, x, n), "ms_set_vec");
+  double res = 0, err = 0;
+  must (ms_residual (c, &res, &err), "ms_residual");
+  if (r)
+    must (ms_get_vec (c, MS_VEC_R, r, n), "ms_get_vec");
+}
+
+bool
+check_res (int root, int loc_res)
+{
+  static int failures = 0;
+  // every rank already holds the agreed verdict (ncclAllReduce inside the library)
+  if (loc_res <= 0)
+    return 0;
+  failures++;
+  printf_root (root, "Cant apply cholesky decomposition er%d\n", failures);
+  return 1;
+}
+
+void
+printf_root (int root, const char *format, ...)
+{
+  if (ms_rt_rank () != root)
+    return;
+  va_list args;
+  va_start (args, format);
+  vprintf (format, args);
+  va_end (args);
+}

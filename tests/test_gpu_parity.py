@@ -1,0 +1,361 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against
+  (1) the oracle (oracle/ms_oracle.c) on the same inputs,
+  (2) the committed goldens generated from the unmodified reference (tests/golden/),
+  (3) size-independent properties at the BASELINE sizes (planted solution, analytic factor).
+
+Tolerances (fp64, eps = 2^-52), as BASELINE.json's north star states them:
+  factor   : max|R_gpu - R_ref| / max|R_ref|  <=  C * n * eps * cond(A)
+  solution : ||x_gpu - x*||_2 no worse than max(2 * the reference's `er`, C * n * eps * cond * ||x*||)
+  residual : ||A x - b||_2 / ||b||_2 no worse than the reference's (x2 slack for rounding noise)
+with C = 10.  For the formula matrix A_ij = n - max(i,j), cond_2(A) ~ 1.62 n^2.
+The block-level kernels that keep the reference's operation order are held to BIT equality.
+"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+EPS = 2.0 ** -52
+C_TOL = 10.0
+
+
+@pytest.fixture(scope="module")
+def ms():
+    import matrix_solver_b200 as m
+    if m.device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on a B200 box")
+    return m
+
+
+@pytest.fixture(scope="module")
+def ora():
+    return ol.Oracle()
+
+
+DUMPS = np.load(os.path.join(ol.GOLDEN_DIR, "ref_dumps.npz"))
+CASES = sorted({k.split("/")[0] for k in DUMPS.files})
+with open(os.path.join(ol.GOLDEN_DIR, "ref_summary.json")) as f:
+    SUMMARY = json.load(f)
+
+
+def golden(case):
+    return {k.split("/", 1)[1]: DUMPS[k] for k in DUMPS.files if k.startswith(case + "/")}
+
+
+def fixture_path(case):
+    stem = case.split("_m")[0]
+    return None if stem.startswith("formula") else os.path.join(ol.FIXTURE_DIR, stem + ".txt")
+
+
+def rel(a, b):
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (den if den else 1.0))
+
+
+def gpu_pipeline(ms, n, m, path=None, dense=None, options=(), want_matrices=True):
+    """test_mat's flow (test/test_mat.cpp:89-165) on the device."""
+    out = {}
+    with ms.Solver(n, m) as s:
+        for k, v in options:
+            s.set_option(k, v)
+
+        def fill():
+            if dense is not None:
+                s.upload_rows(dense)
+            elif path:
+                a, st = ol.Oracle().init_file(n, path)
+                assert st == 1
+                s.upload_rows(a)
+            else:
+                s.init_formula(0)
+        fill()
+        if want_matrices:
+            out["A"] = s.get_upper()
+        out["norm"] = s.b_and_norm()
+        out["b"] = s.get_vec("b")
+        fail, out["elapsed"] = s.factor(out["norm"])
+        out["factor_fail"] = fail
+        if fail:
+            return out
+        if want_matrices:
+            out["R"] = s.get_upper()
+        out["d"] = s.get_vec("d")
+        out["forward_fail"] = s.solve_forward(out["norm"])
+        out["backward_fail"] = s.solve_backward(out["norm"])
+        out["y"], out["x"] = s.get_vec("y"), s.get_vec("x")
+        fill()
+        out["residual"], out["error"] = s.residual()
+        out["r"] = s.get_vec("r")
+        out["stats"] = s.stats()
+    return out
+
+
+def cond_estimate(A_upper):
+    a = np.triu(A_upper) + np.triu(A_upper, 1).T
+    return np.linalg.cond(a)
+
+
+# --------------------------------------------------------------------------- block kernels
+@pytest.mark.parametrize("w", [1, 2, 3, 7, 16, 31, 48, 64, 96, 112])
+def test_diag_factor_and_inverse_bit_exact(ms, ora, w):
+    """K1/K2 keep the reference's operation order: bit-identical to the oracle (which is pinned
+    bit-identical to the reference's cholesky_decomp_U / reverse_upper)."""
+    rng = np.random.default_rng(100 + w)
+    g = rng.standard_normal((w, w))
+    spd = g @ g.T + w * np.eye(w)
+    if w > 2:
+        spd[w // 2:, w // 2:] *= -1      # indefinite: exercises d = -1
+    blk = np.triu(spd)
+    norma = np.abs(spd).sum(1).max()
+    r0, d0, f0 = ora.diag_factor(blk, norma)
+    r1, d1, f1 = ms.block_diag_factor(blk, norma)
+    assert f0 == f1 == 0
+    assert np.array_equal(d0, d1)
+    assert np.array_equal(np.triu(r0), r1)
+    i0, g0 = ora.upper_inverse(np.triu(r0), norma)
+    i1, g1 = ms.block_upper_inverse(np.triu(r0), norma)
+    assert g0 == g1 == 0 and np.array_equal(np.triu(i0), i1)
+
+
+def test_diag_factor_failure_verdicts(ms, ora):
+    """Quirks of src/solver.cpp:117-125: pre-update pivot test, sgn(0) = -1,
+    thresholds relative to the norm."""
+    for blk, norma in [
+        (np.array([[1.0, 1.0], [0.0, 0.0]]), 2.0),            # a_11 == 0 before the update -> fail
+        (np.array([[1.0, 1.0], [0.0, 1.0]]), 2.0),            # pivot becomes 0 -> fail
+        (np.array([[4.0, 2.0], [0.0, 3.0]]), 6.0),            # fine
+        (np.array([[4e-20, 2e-20], [0.0, 3e-20]]), 6e-20),    # tiny but relative -> fine
+        (np.array([[1e-16, 0.0], [0.0, 1.0]]), 1.0),          # below EPS*norm -> fail
+    ]:
+        _, _, f0 = ora.diag_factor(blk, norma)
+        _, _, f1 = ms.block_diag_factor(blk, norma)
+        assert f0 == f1
+
+
+@pytest.mark.parametrize("k,h,w", [(1, 1, 1), (3, 3, 3), (3, 3, 1), (8, 8, 13), (33, 33, 33), (64, 64, 64),
+                                   (64, 64, 5), (100, 100, 37), (48, 48, 200)])
+def test_block_update_and_panel(ms, ora, k, h, w):
+    rng = np.random.default_rng(k * 1000 + w)
+    A = rng.standard_normal((h, w))
+    R1 = rng.standard_normal((k, h))
+    R2 = rng.standard_normal((k, w))
+    D = np.where(rng.random(k) < 0.3, -1.0, 1.0)
+    want = ora.update(A, R1, D, R2)
+    scale = np.abs(R1).T @ np.abs(R2) + np.abs(A)           # componentwise bound
+    assert np.all(np.abs(ms.block_update(A, R1, D, R2) - want) <= 4 * k * EPS * scale)
+    inv = np.triu(rng.standard_normal((h, h)))
+    Dh = np.where(rng.random(h) < 0.3, -1.0, 1.0)
+    want = ora.panel(inv, A, Dh)
+    scale = np.abs(inv).T @ np.abs(A)
+    assert np.all(np.abs(ms.block_panel(inv, A, Dh) - want) <= 4 * h * EPS * scale + 1e-300)
+    Aup = np.triu(rng.standard_normal((w, w)))
+    R = rng.standard_normal((k, w))
+    want = np.triu(ora.update(Aup, R, D, R, True))
+    got = ms.block_update_diag(Aup, R, D)
+    scale = np.abs(R).T @ np.abs(R) + np.abs(Aup)
+    assert np.all(np.abs(got - want) <= 4 * k * EPS * scale)
+
+
+def test_vector_norms(ms, ora):
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 7, 1000, 4097):
+        v = rng.standard_normal(n)
+        assert ms.norm2(v) == pytest.approx(ora.norm2(v), rel=1e-14)
+        assert ms.error_vs_planted(v) == pytest.approx(ora.error(v), rel=1e-14)
+
+
+# --------------------------------------------------------------------------- whole pipeline, small
+@pytest.mark.parametrize("case", CASES)
+def test_pipeline_against_reference_golden(ms, case):
+    g = golden(case)
+    n, m = int(g["n"]), int(g["m"])
+    o = gpu_pipeline(ms, n, m, fixture_path(case))
+    assert np.array_equal(np.triu(o["A"]), g["A"])
+    assert o["norm"] == pytest.approx(float(g["norm"]), rel=4 * EPS)
+    assert np.allclose(o["b"], g["b"], rtol=n * EPS, atol=n * EPS * float(g["norm"]))
+    assert o["factor_fail"] == bool(g["factor_fail"])      # incl. b/c/d.txt: "Cant apply ..."
+    if o["factor_fail"]:
+        return
+    cond = cond_estimate(g["A"])
+    tol = C_TOL * n * EPS * cond
+    assert np.array_equal(o["d"], g["d"])                   # f.txt: d = (1, 1, -1, 1)
+    assert rel(np.triu(o["R"]), g["R"]) <= tol
+    assert not o["forward_fail"] and not o["backward_fail"]
+    assert rel(o["y"], g["y"]) <= tol
+    xstar = np.array([1.0 if i % 2 == 0 else 0.0 for i in range(n)])
+    assert o["error"] <= max(2 * float(g["error"]), tol * np.linalg.norm(xstar))
+    bn = np.linalg.norm(g["b"])
+    assert o["residual"] / bn <= max(2 * float(g["residual"]) / bn, 8 * n * EPS)
+
+
+@pytest.mark.parametrize("n,m", [(3, 3), (5, 1), (9, 2), (17, 5), (30, 30), (33, 64), (65, 64), (127, 64),
+                                 (129, 64), (192, 64), (200, 64), (257, 128), (300, 100), (511, 192)])
+def test_pipeline_against_oracle_formula_sweep(ms, ora, n, m):
+    """The reference's own sweep idea (test_data/test13_mpi.sh): many (n, m), incl. n % m != 0,
+    m > n, m == n — both kernel families (m % 64 == 0 -> DMMA tiles, otherwise generic)."""
+    o = gpu_pipeline(ms, n, m)
+    w = ora.solve_pipeline(n, m)
+    assert np.array_equal(np.triu(o["A"]), np.triu(w["A"]))
+    assert o["norm"] == w["norm"] and np.array_equal(o["b"], w["b"])   # integer data: exact
+    assert not o["factor_fail"] and np.array_equal(o["d"], w["d"])
+    tol = C_TOL * n * EPS * 1.62 * n * n
+    assert rel(np.triu(o["R"]), np.triu(w["R"])) <= tol
+    assert rel(o["y"], w["y"]) <= tol and rel(o["x"], w["x"]) <= tol
+    assert o["error"] <= max(2 * w["error"], tol * np.sqrt(n))
+    assert o["residual"] <= max(2 * w["residual"], 8 * n * EPS * np.linalg.norm(w["b"]))
+    assert o["stats"]["used_dmma"] == (1 if (m % 64 == 0 and n > 64) else 0)
+
+
+@pytest.mark.parametrize("opts", [(("force_generic", 1),), (("lookahead", 0),), (("force_generic", 1), ("lookahead", 0))])
+def test_kernel_families_and_schedules_agree(ms, opts):
+    """DMMA tiles vs generic DFMA kernel, look-ahead vs in-order: same factor within rounding."""
+    n, m = 640, 128
+    base = gpu_pipeline(ms, n, m)
+    alt = gpu_pipeline(ms, n, m, options=opts)
+    tol = C_TOL * n * EPS * 1.62 * n * n
+    assert rel(np.triu(alt["R"]), np.triu(base["R"])) <= tol
+    assert rel(alt["x"], base["x"]) <= tol
+    if ("lookahead", 0) in opts and ("force_generic", 1) not in opts:
+        assert np.array_equal(alt["R"], base["R"])           # scheduling must not change arithmetic
+
+
+def test_indefinite_and_random_spd_dense(ms, ora):
+    """Non-formula inputs through the upload path: random SPD and an indefinite matrix with
+    non-zero leading minors (D has -1 entries)."""
+    rng = np.random.default_rng(11)
+    n, m = 200, 64
+    g = rng.standard_normal((n, n))
+    spd = g @ g.T / n + np.eye(n)
+    sign = np.where(np.arange(n) % 5 == 3, -1.0, 1.0)
+    L = np.tril(rng.standard_normal((n, n)) * 0.1, -1) + np.eye(n)
+    indef = L @ np.diag(sign * (1 + rng.random(n))) @ L.T
+    for mat in (spd, indef):
+        a = np.triu(mat)
+        b, norm = ora.b_norm(a)
+        r_ref, d_ref, f_ref = ora.factor(a, m, norm)
+        o = gpu_pipeline(ms, n, m, dense=a)
+        assert not f_ref and not o["factor_fail"]
+        assert np.array_equal(o["d"], d_ref)
+        cond = np.linalg.cond(mat)
+        assert rel(np.triu(o["R"]), np.triu(r_ref)) <= C_TOL * n * EPS * cond
+        assert np.allclose(o["b"], b, rtol=1e-13, atol=1e-13 * norm)
+        x_ref = np.array([1.0 if i % 2 == 0 else 0.0 for i in range(n)])
+        assert np.linalg.norm(o["x"] - x_ref) <= C_TOL * n * EPS * cond * np.linalg.norm(x_ref)
+    assert np.any(d_ref < 0)
+
+
+def test_packed_layout_round_trip(ms, ora):
+    """ms_upload_packed / ms_download_packed speak the reference's packed block-column layout
+    (src/init.cpp:29-98): encode -> device -> decode is the identity, element by element."""
+    for n, m in [(4, 3), (10, 7), (100, 48), (200, 64), (130, 64), (64, 128)]:
+        a = ora.init_formula(n) + np.triu(np.arange(n * n, dtype=float).reshape(n, n)) * 1e-3
+        body = np.zeros(n * (n + 1) // 2)
+        for i in range(n):
+            for j in range(i, n):
+                body[ora.packed_offset(i, j, n, m)] = a[i, j]
+        with ms.Solver(n, m) as s:
+            s.upload_packed(body)
+            assert np.array_equal(np.triu(s.get_upper()), np.triu(a))
+            back = np.zeros_like(body)
+            s.download_packed(back)
+            assert np.array_equal(back, body)
+            # gather_col semantics (src/init.cpp:446-490)
+            for j in (0, n // 2, n - 1):
+                assert np.array_equal(s.get_col(j)[: j + 1], a[: j + 1, j])
+
+
+# --------------------------------------------------------------------------- larger sizes
+@pytest.mark.parametrize("case", sorted(SUMMARY))
+def test_large_formula_against_reference_summary(ms, case):
+    s = SUMMARY[case]
+    n, m = s["n"], s["m"]
+    o = gpu_pipeline(ms, n, m, want_matrices=False)
+    assert o["norm"] == s["norm"]
+    assert not o["factor_fail"] and np.all(o["d"] == 1.0)
+    tol = C_TOL * n * EPS * 1.62 * n * n
+    assert np.allclose(o["x"][:16], s["x_head"], atol=tol)
+    assert o["error"] <= max(2 * s["error"], tol * np.sqrt(n / 2))
+    assert o["residual"] <= 2 * s["residual"]
+    idx = np.array(s["sample_idx"])
+    with ms.Solver(n, m) as sv:
+        sv.init_formula(0)
+        sv.factor(sv.b_and_norm())
+        got = np.array([sv.get_row(int(i))[idx] for i in idx]) * (idx[:, None] <= idx[None, :])
+    assert rel(got, np.array(s["R_samples"])) <= tol
+
+
+@pytest.mark.parametrize("n,m", [(4096, 64), (16384, 128), (16384, 256)])
+def test_baseline_sizes_properties(ms, n, m):
+    """BASELINE configs 2 and 3 via size-independent properties: planted solution x* = (1,0,1,0,..),
+    d = 1, ||A||_inf = n(n+1)/2, analytic factor R_0j = (n-j)/sqrt(n),
+    R_ij = (n-j)/sqrt((n-i)(n-i+1)), residual no worse than the reference's."""
+    ref = {(4096, 64): (3.097032e-07, 6.317555e-07), (16384, 128): (8.798242e-06, 1.851129e-05),
+           (16384, 256): (8.798242e-06, 1.851129e-05)}[(n, m)]      # BASELINE.md §2 (m=256: same scale)
+    with ms.Solver(n, m) as s:
+        s.init_formula(0)
+        norm = s.b_and_norm()
+        assert norm == n * (n + 1) / 2
+        fail, _ = s.factor(norm)
+        assert not fail
+        assert np.all(s.get_vec("d") == 1.0)
+        tol = C_TOL * n * EPS * 1.62 * n * n
+        for i in (0, 1, 63, 64, n // 2 - 1, n // 2, n - 65, n - 1):
+            row = s.get_row(i)[i:]
+            j = np.arange(i, n, dtype=float)
+            want = (n - j) / (np.sqrt(n) if i == 0 else np.sqrt((n - i) * (n - i + 1.0)))
+            assert rel(row, want) <= tol
+        assert not s.solve_forward(norm) and not s.solve_backward(norm)
+        s.init_formula(0)
+        res, err = s.residual()
+        assert err <= max(2 * ref[1], tol * np.sqrt(n / 2))
+        assert res <= 2 * ref[0]
+        st = s.stats()
+        assert st["used_dmma"] == 1 and st["kernel_launches"] > 0
+
+
+def test_cli_stdout_matches_reference(ms, tmp_path):
+    """The drop-in CLI prints what the reference prints (tests/golden/cli/*.txt from the unmodified
+    reference); numeric fields are compared as numbers, `elapsed` is ignored."""
+    exe = os.path.join(ol.ROOT, "matrix_solver_b200", "bin", "test_mat")
+    assert os.path.exists(exe), "run `make cli`"
+    import re
+    num = re.compile(r"-?\d+\.\d+(?:e[+-]\d+)?")
+    shape = re.compile(r"[ -]?\d+\.\d+(?:e[+-]\d+)?")    # a sign occupies the pad blank
+    for case in ["a_m3", "a20_m3", "b_m3", "c_m3", "d_m3", "e_m3", "f_m3", "a_m7", "formula_n10_m7",
+                 "formula_n30_m9", "formula_n100_m48", "formula_n130_m64", "formula_n200_m64"]:
+        g = golden(case)
+        args = [exe, str(int(g["n"])), str(int(g["m"]))]
+        fx = fixture_path(case)
+        if fx:
+            args.append(os.path.relpath(fx, ol.ROOT))
+        got = subprocess.run(args, cwd=ol.ROOT, capture_output=True, text=True, check=True).stdout
+        want = open(os.path.join(ol.GOLDEN_DIR, "cli", case + ".txt")).read()
+        gl, wl = got.strip().split("\n"), want.strip().split("\n")
+        assert len(gl) == len(wl), (case, got, want)
+        for a, b in zip(gl, wl):
+            a2, b2 = a.split(", elapsed")[0], b.split(", elapsed")[0]
+            # same tokens in the same order: text must match, numbers are compared as numbers
+            ta, tb = a2.split(), b2.split()
+            assert len(ta) == len(tb), (case, a, b)
+            for x, y in zip(ta, tb):
+                if num.fullmatch(x.rstrip(",")) and num.fullmatch(y.rstrip(",")):
+                    continue
+                assert x == y, (case, a, b)
+            if "-" not in num.sub("", a2) + num.sub("", b2) and not re.search(r"\d-|\s-\d", a2 + b2):
+                # no minus signs anywhere: the column layout must be identical character by character
+                assert shape.sub("#", a2) == shape.sub("#", b2), (case, a, b)
+            fa, fb = [float(v) for v in num.findall(a2)], [float(v) for v in num.findall(b2)]
+            if "residual" in a2:
+                # n, m are integers (not matched); residual and er: same order of magnitude
+                assert fa[0] <= max(4 * fb[0], 1e-13) and fa[1] <= max(4 * fb[1], 1e-12), (case, a, b)
+            else:
+                assert np.allclose(fa, fb, rtol=2e-2, atol=1e-5), (case, a, b)
+    lg = os.path.join(ol.ROOT, "log.txt")
+    assert os.path.exists(lg)
+    os.remove(lg)

@@ -69,6 +69,7 @@ def run_pipeline(n, m, path=None, generic=False, lookahead=True, compare=True, d
     with ms.Solver(n, m) as s:
         s.set_option("force_generic", generic)
         s.set_option("lookahead", lookahead)
+        s.set_option("profile_update", int(os.environ.get("MS_PROFILE_UPDATE", "0")))
         if path or dense is not None:
             a = dense
             if a is None:
@@ -97,7 +98,10 @@ def run_pipeline(n, m, path=None, generic=False, lookahead=True, compare=True, d
                        d_neg=int(np.sum(d < 0)), x_head=[float(v) for v in x[:4]])
         st = s.stats()
         out["stats"] = {k: st[k] for k in ("factor_ms", "forward_ms", "backward_ms", "init_ms", "bnorm_ms",
-                                           "residual_ms", "kernel_launches", "used_dmma")}
+                                           "residual_ms", "kernel_launches", "used_dmma", "update_ms", "update_flops",
+                                           "update_launches")}
+        if st["update_ms"] > 0:
+            out["update_tflops"] = st["update_flops"] / st["update_ms"] / 1e9
         if compare and n <= 2048:
             ora = ol.Oracle()
             o = ora.solve_pipeline(n, m, path) if dense is None else None
@@ -147,11 +151,16 @@ def stage_mid():
 def stage_big():
     for n, m in [(16384, 128), (16384, 256), (32768, 256)]:
         run_pipeline(n, m, compare=False)
+        run_pipeline(n, m, compare=False, lookahead=False)
+
+
+def stage_huge():
+    run_pipeline(65536, 256, compare=False)
 
 
 STAGES = {"probe": stage_probe, "blocks": stage_blocks, "small_generic": stage_small_generic,
           "fast_small": stage_fast_small, "fast_vs_generic": stage_fast_vs_generic, "mid": stage_mid,
-          "big": stage_big}
+          "big": stage_big, "huge": stage_huge}
 
 
 def main():
