@@ -61,7 +61,9 @@ diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *
     }
   __syncthreads ();
 
-  // ---- K1: signed Cholesky, right-looking inside the piece
+  // ---- K1: signed Cholesky, right-looking inside the piece (16 x 16 thread grid over the
+  // trailing square; no integer divisions on the critical path)
+  const int tx = tid & 15, ty = tid >> 4;
   for (int i = 0; i < h; i++)
     {
       double s = a[i * S + i];
@@ -78,13 +80,12 @@ diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *
       for (int j = i + 1 + tid; j < h; j += 256)
         a[i * S + j] = __ddiv_rn (a[i * S + j], den);
       __syncthreads ();
-      int cnt = h - i - 1;
-      for (int e = tid; e < cnt * cnt; e += 256)
+      for (int k = i + 1 + ty; k < h; k += 16)
         {
-          int k = i + 1 + e / cnt, j = i + 1 + e % cnt;
-          if (j >= k)
-            a[k * S + j] = __dsub_rn (a[k * S + j],
-                                      __dmul_rn (__dmul_rn (a[i * S + k], a[i * S + j]), di));
+          const double aik = a[i * S + k];
+          for (int j = i + 1 + tx; j < h; j += 16)
+            if (j >= k)
+              a[k * S + j] = __dsub_rn (a[k * S + j], __dmul_rn (__dmul_rn (aik, a[i * S + j]), di));
         }
       __syncthreads ();
     }

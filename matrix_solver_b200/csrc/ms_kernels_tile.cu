@@ -25,6 +25,8 @@
 // "tile kernel"; in short a lane (p = lane/4, q = lane%4) loads with ONE 16-byte LDS the two
 // neighbouring columns 2p, 2p+1 of k-row 8g+2q+e, which under the 128B swizzle sit in 16-byte
 // slot (p ^ (2q+e)) of that row: the 8 lanes of every quarter warp hit 8 distinct slots.
+#include <algorithm>
+
 #include "ms_common.cuh"
 
 #define LAUNCH_COUNT(c) ((c)->stats.kernel_launches++)
@@ -47,46 +49,72 @@ struct tile_args
   // the block-row cyclic map.  MODE_PANEL: single row tile, g0 = global row of the piece.
   size_t lrow_begin, m;
   int rank, nranks;
+  int n_row_tiles;
   size_t g0;
-  size_t col_tile0;         // first column tile (units of MS_BN) of the launch
+  size_t col_tile0;         // MODE_PANEL: first column tile (units of MS_BN)
   size_t col_lo_panel;      // MODE_PANEL: first column to write
   size_t n;                 // columns >= n are never written
+  int tiles_per_cta;        // consecutive tiles one CTA walks before it retires
 };
 
 constexpr int TILE_A_BYTES = (MS_BM / MS_CHUNK) * MS_KC * MS_CHUNK * 8;  // 8 KB
 constexpr int TILE_B_BYTES = (MS_BN / MS_CHUNK) * MS_KC * MS_CHUNK * 8;  // 16 KB
 constexpr int TILE_STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;            // 24 KB
 constexpr int TILE_CHUNK_BYTES = MS_KC * MS_CHUNK * 8;                   // 2 KB
-constexpr int TILE_MAX_K = 2048;
+constexpr int TILE_MAX_K = 1024;
+constexpr int TILE_MAX_RT = 2048;  // row tiles per launch (the host splits larger ranges)
 constexpr int TILE_SMEM_BYTES = MS_STAGES * TILE_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/
-                                + TILE_MAX_K * 4;
+                                + TILE_MAX_K * 4 + (TILE_MAX_RT + 2) * 4;
 
+// global row of row tile rt / number of column tiles it owns (host and device agree on these)
+__host__ __device__ __forceinline__ size_t
+tile_row_global (const tile_args &ta, int mode, int rt)
+{
+  if (mode != MS_MODE_UPDATE)
+    return ta.g0;
+  const size_t l = ta.lrow_begin + (size_t)rt * MS_BM;
+  const size_t lb = l / ta.m;
+  return (lb * (size_t)ta.nranks + (size_t)ta.rank) * ta.m + (l - lb * ta.m);
+}
+
+__host__ __device__ __forceinline__ size_t
+tile_first_col_tile (const tile_args &ta, int mode, size_t g)
+{
+  return mode == MS_MODE_UPDATE ? g / MS_BN : ta.col_tile0;
+}
+
+__host__ __device__ __forceinline__ int
+tile_count_in_row (const tile_args &ta, int mode, int rt)
+{
+  const size_t g = tile_row_global (ta, mode, rt);
+  if (g >= ta.n)
+    return 0;
+  const size_t total = (ta.n + MS_BN - 1) / MS_BN;
+  const size_t first = tile_first_col_tile (ta, mode, g);
+  return first < total ? (int)(total - first) : 0;
+}
+
+// Each CTA walks `tiles_per_cta` consecutive entries of the list of stored tiles (same row tile =
+// same A operand for neighbours).  The TMA ring keeps running across those tiles, so the producer is
+// already fetching the next tile's operands while the consumers run the current tile's epilogue.
+// CTAs are deliberately NOT persistent for the whole launch: retiring every few tiles lets the
+// hardware scheduler hand SM slots to the high-priority panel stream (look-ahead) and keeps the two
+// CTAs that share an SM out of phase, so one CTA's epilogue overlaps the other's DMMA loop.
 template <int MODE>
 __global__ void __launch_bounds__ (MS_TILE_THREADS, 2)
 tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const tile_args ta)
 {
-  const int rt = blockIdx.y;                                   // row tile
-  const size_t ct = ta.col_tile0 + blockIdx.x;                 // column tile (global, units of 128)
-  size_t g_row0 = ta.g0;                                       // global row of tile row 0
-  if (MODE == MS_MODE_UPDATE)
-    {
-      const size_t l = ta.lrow_begin + (size_t)rt * MS_BM;
-      const size_t lb = l / ta.m;
-      g_row0 = (lb * (size_t)ta.nranks + (size_t)ta.rank) * ta.m + (l - lb * ta.m);
-    }
-  const size_t col0 = ct * MS_BN;
-  if (MODE == MS_MODE_UPDATE && (col0 + MS_BN <= g_row0 || g_row0 >= ta.n))
-    return;  // tile entirely left of the diagonal block (not stored) or below the matrix
-
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t *full_bar = (uint64_t *)(smem + MS_STAGES * TILE_STAGE_BYTES);
   uint64_t *empty_bar = full_bar + MS_STAGES;
   uint32_t *sgn = (uint32_t *)(empty_bar + MS_STAGES + 8);
+  int *pref = (int *)(sgn + TILE_MAX_K);  // pref[rt] = tiles in row tiles < rt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = ta.K / MS_KC;
+  const int n_rt = ta.n_row_tiles;
 
   if (threadIdx.x == 0)
     {
@@ -97,165 +125,251 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       mbar_fence_init ();
     }
+  int my_neg = 0;
   for (int k = threadIdx.x; k < ta.K; k += MS_TILE_THREADS)
-    sgn[k] = (ta.dsign != nullptr && ta.dsign[k] < 0.0) ? 0x80000000u : 0u;
-  __syncthreads ();
-
-  if (warp == MS_TILE_CONSUMER_WARPS)
     {
-      // ------------------------------------------------------------------ TMA producer
-      if (lane == 0)
+      const bool neg = ta.dsign != nullptr && ta.dsign[k] < 0.0;
+      sgn[k] = neg ? 0x80000000u : 0u;
+      my_neg |= neg;
+    }
+  for (int rt = threadIdx.x; rt < n_rt; rt += MS_TILE_THREADS)
+    pref[rt + 1] = tile_count_in_row (ta, MODE, rt);
+  const bool any_neg = __syncthreads_or (my_neg) != 0;
+  if (warp == 0)
+    {
+      // exclusive scan of pref[1..n_rt] by one warp: lane-contiguous segments
+      const int seg = (n_rt + 31) / 32;
+      const int b = lane * seg, e = min (b + seg, n_rt);
+      int sum = 0;
+      for (int i = b; i < e; i++)
+        sum += pref[i + 1];
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
         {
-          tma_prefetch_desc (&tmA);
-          tma_prefetch_desc (&tmB);
-          // A chunk 0 = the 16 columns of the panel that match the tile's first output row
-          const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(g_row0 / MS_CHUNK) : 0;
-          const int ax = ta.ax0 + achunk0 * ta.axs, ay = ta.ay0 + achunk0 * ta.ays;
-          const int bchunk0 = (int)(ct * (MS_BN / MS_CHUNK));
-          for (int kb = 0; kb < nkb; kb++)
+          int v = __shfl_up_sync (0xffffffffu, incl, o);
+          if (lane >= o)
+            incl += v;
+        }
+      int run = incl - sum;
+      for (int i = b; i < e; i++)
+        {
+          int c = pref[i + 1];
+          pref[i + 1] = run + c;  // inclusive
+          run += c;
+        }
+      if (lane == 0)
+        pref[0] = 0;
+    }
+  __syncthreads ();
+  const int total_tiles = pref[n_rt];
+
+  const int p = lane >> 2, q = lane & 3;
+  const int wm = warp >> 2;  // consumer rows  wm*32
+  const int wn = warp & 3;   // consumer cols  wn*32
+  uint32_t it = 0;           // running k-stage counter (same sequence in producer and consumers)
+
+  const int t_begin = blockIdx.x * ta.tiles_per_cta;
+  const int t_end = min (total_tiles, t_begin + ta.tiles_per_cta);
+  for (int t = t_begin; t < t_end; t++)
+    {
+      int lo = 0, hi = n_rt - 1;
+      while (lo < hi)
+        {
+          const int mid = (lo + hi + 1) >> 1;
+          if (pref[mid] <= t)
+            lo = mid;
+          else
+            hi = mid - 1;
+        }
+      const int rt = lo;
+      const size_t g_row0 = tile_row_global (ta, MODE, rt);
+      const size_t ct = tile_first_col_tile (ta, MODE, g_row0) + (size_t)(t - pref[rt]);
+      const size_t col0 = ct * MS_BN;
+
+      if (warp == MS_TILE_CONSUMER_WARPS)
+        {
+          // ---------------------------------------------------------------- TMA producer
+          if (lane == 0)
             {
-              const int s = kb % MS_STAGES;
-              const uint32_t ph = (uint32_t)((kb / MS_STAGES) & 1);
-              mbar_wait (&empty_bar[s], ph ^ 1u);
-              mbar_arrive_expect_tx (&full_bar[s], TILE_STAGE_BYTES);
-              uint8_t *sa = smem + s * TILE_STAGE_BYTES;
-              uint8_t *sb = sa + TILE_A_BYTES;
-              const int kk = kb * MS_KC;
+              // A chunk 0 = the 16 panel columns that match the tile's first output row
+              const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(g_row0 / MS_CHUNK) : 0;
+              const int ax = ta.ax0 + achunk0 * ta.axs, ay = ta.ay0 + achunk0 * ta.ays;
+              const int bchunk0 = (int)(ct * (MS_BN / MS_CHUNK));
+              for (int kb = 0; kb < nkb; kb++, it++)
+                {
+                  const int s = it % MS_STAGES;
+                  const uint32_t ph = (it / MS_STAGES) & 1u;
+                  mbar_wait (&empty_bar[s], ph ^ 1u);
+                  mbar_arrive_expect_tx (&full_bar[s], TILE_STAGE_BYTES);
+                  uint8_t *sa = smem + s * TILE_STAGE_BYTES;
+                  uint8_t *sb = sa + TILE_A_BYTES;
+                  const int kk = kb * MS_KC;
 #pragma unroll
-              for (int ci = 0; ci < MS_BM / MS_CHUNK; ci++)
-                tma_load_2d (sa + ci * TILE_CHUNK_BYTES, &tmA, ax + ci * ta.axs, ay + ci * ta.ays + kk,
-                             &full_bar[s]);
+                  for (int ci = 0; ci < MS_BM / MS_CHUNK; ci++)
+                    tma_load_2d (sa + ci * TILE_CHUNK_BYTES, &tmA, ax + ci * ta.axs, ay + ci * ta.ays + kk,
+                                 &full_bar[s]);
 #pragma unroll
-              for (int cj = 0; cj < MS_BN / MS_CHUNK; cj++)
-                tma_load_2d (sb + cj * TILE_CHUNK_BYTES, &tmB, ta.bx0 + (bchunk0 + cj) * ta.bxs,
-                             ta.by0 + (bchunk0 + cj) * ta.bys + kk, &full_bar[s]);
+                  for (int cj = 0; cj < MS_BN / MS_CHUNK; cj++)
+                    tma_load_2d (sb + cj * TILE_CHUNK_BYTES, &tmB, ta.bx0 + (bchunk0 + cj) * ta.bxs,
+                                 ta.by0 + (bchunk0 + cj) * ta.bys + kk, &full_bar[s]);
+                }
+            }
+          continue;
+        }
+
+      // -------------------------------------------------------------------- DMMA consumers
+      const int rows_valid = g_row0 + MS_BM <= ta.n ? MS_BM : (int)(ta.n - g_row0);
+      const size_t col_lo = (MODE == MS_MODE_UPDATE) ? g_row0 : ta.col_lo_panel;
+      double *Ct = ta.C + (size_t)rt * MS_BM * ta.ldc;
+      if (MODE == MS_MODE_UPDATE)
+        {
+          // the C tile is touched exactly once per launch and comes from HBM: start pulling this
+          // warp's 32 x 32 patch into L2 now so that the epilogue's loads find it there
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            {
+              const int r = wm * 32 + p * 4 + i;       // 8 lanes groups x 4 rows = 32 rows
+              const size_t cc = col0 + wn * 32 + q * 8; // 4 x 64 B = the patch's 256 B row segment
+              if (r < rows_valid && cc < ta.n)
+                asm volatile ("prefetch.global.L2 [%0];" ::"l"(Ct + (size_t)r * ta.ldc + cc));
             }
         }
-      return;
-    }
-
-  // ---------------------------------------------------------------------- DMMA consumers
-  const int wm = warp >> 2;  // 0..1 : rows  wm*32
-  const int wn = warp & 3;   // 0..3 : cols  wn*32
-  const int p = lane >> 2, q = lane & 3;
-
-  double acc[2][2][2][2][2];  // [ib][jb][a][b][e]
+      double acc[2][2][2][2][2];  // [ib][jb][a][b][e]
 #pragma unroll
-  for (int i = 0; i < 32; i++)
-    (&acc[0][0][0][0][0])[i] = 0.0;
+      for (int i = 0; i < 32; i++)
+        (&acc[0][0][0][0][0])[i] = 0.0;
 
-  for (int kb = 0; kb < nkb; kb++)
-    {
-      const int s = kb % MS_STAGES;
-      const uint32_t ph = (uint32_t)((kb / MS_STAGES) & 1);
-      mbar_wait (&full_bar[s], ph);
-      const uint8_t *sa = smem + s * TILE_STAGE_BYTES + (wm * 2) * TILE_CHUNK_BYTES;
-      const uint8_t *sb = smem + s * TILE_STAGE_BYTES + TILE_A_BYTES + (wn * 2) * TILE_CHUNK_BYTES;
-#pragma unroll
-      for (int g = 0; g < MS_KC / 8; g++)
+      for (int kb = 0; kb < nkb; kb++, it++)
         {
+          const int s = it % MS_STAGES;
+          const uint32_t ph = (it / MS_STAGES) & 1u;
+          mbar_wait (&full_bar[s], ph);
+          const uint8_t *sa = smem + s * TILE_STAGE_BYTES + (wm * 2) * TILE_CHUNK_BYTES;
+          const uint8_t *sb = smem + s * TILE_STAGE_BYTES + TILE_A_BYTES + (wn * 2) * TILE_CHUNK_BYTES;
 #pragma unroll
-          for (int e = 0; e < 2; e++)
+          for (int g = 0; g < MS_KC / 8; g++)
             {
-              const int kr = 8 * g + 2 * q + e;                    // k row inside the stage
-              const int off = kr * 128 + ((p ^ (kr & 7)) << 4);    // swizzled 16-byte slot
-              double2 fa[2], fb[2];
 #pragma unroll
-              for (int ib = 0; ib < 2; ib++)
-                fa[ib] = *reinterpret_cast<const double2 *> (sa + ib * TILE_CHUNK_BYTES + off);
-#pragma unroll
-              for (int jb = 0; jb < 2; jb++)
-                fb[jb] = *reinterpret_cast<const double2 *> (sb + jb * TILE_CHUNK_BYTES + off);
-              if (MODE == MS_MODE_UPDATE)
+              for (int e = 0; e < 2; e++)
                 {
-                  const uint32_t sm = sgn[kb * MS_KC + kr];
+                  const int kr = 8 * g + 2 * q + e;                    // k row inside the stage
+                  const int off = kr * 128 + ((p ^ (kr & 7)) << 4);    // swizzled 16-byte slot
+                  double2 fa[2], fb[2];
 #pragma unroll
                   for (int ib = 0; ib < 2; ib++)
+                    fa[ib] = *reinterpret_cast<const double2 *> (sa + ib * TILE_CHUNK_BYTES + off);
+#pragma unroll
+                  for (int jb = 0; jb < 2; jb++)
+                    fb[jb] = *reinterpret_cast<const double2 *> (sb + jb * TILE_CHUNK_BYTES + off);
+                  if (MODE == MS_MODE_UPDATE && any_neg)
                     {
-                      fa[ib].x = flip_sign (fa[ib].x, sm);
-                      fa[ib].y = flip_sign (fa[ib].y, sm);
+                      const uint32_t sm = sgn[kb * MS_KC + kr];
+#pragma unroll
+                      for (int ib = 0; ib < 2; ib++)
+                        {
+                          fa[ib].x = flip_sign (fa[ib].x, sm);
+                          fa[ib].y = flip_sign (fa[ib].y, sm);
+                        }
                     }
+#pragma unroll
+                  for (int ib = 0; ib < 2; ib++)
+#pragma unroll
+                    for (int jb = 0; jb < 2; jb++)
+                      {
+                        dmma_8x8x4 (acc[ib][jb][0][0][0], acc[ib][jb][0][0][1], fa[ib].x, fb[jb].x);
+                        dmma_8x8x4 (acc[ib][jb][0][1][0], acc[ib][jb][0][1][1], fa[ib].x, fb[jb].y);
+                        dmma_8x8x4 (acc[ib][jb][1][0][0], acc[ib][jb][1][0][1], fa[ib].y, fb[jb].x);
+                        dmma_8x8x4 (acc[ib][jb][1][1][0], acc[ib][jb][1][1][1], fa[ib].y, fb[jb].y);
+                      }
                 }
-#pragma unroll
-              for (int ib = 0; ib < 2; ib++)
-#pragma unroll
-                for (int jb = 0; jb < 2; jb++)
-                  {
-                    dmma_8x8x4 (acc[ib][jb][0][0][0], acc[ib][jb][0][0][1], fa[ib].x, fb[jb].x);
-                    dmma_8x8x4 (acc[ib][jb][0][1][0], acc[ib][jb][0][1][1], fa[ib].x, fb[jb].y);
-                    dmma_8x8x4 (acc[ib][jb][1][0][0], acc[ib][jb][1][0][1], fa[ib].y, fb[jb].x);
-                    dmma_8x8x4 (acc[ib][jb][1][1][0], acc[ib][jb][1][1][1], fa[ib].y, fb[jb].y);
-                  }
             }
+          __syncwarp ();
+          if (lane == 0)
+            mbar_arrive (&empty_bar[s]);
         }
-      __syncwarp ();
-      if (lane == 0)
-        mbar_arrive (&empty_bar[s]);
-    }
 
-  // ---------------------------------------------------------------------- epilogue
-  // lane owns, per (ib, jb, a): row wm*32 + 16*ib + 2p + a, columns wn*32 + 16*jb + 4q .. +3
-  const int rows_valid = g_row0 + MS_BM <= ta.n ? MS_BM : (int)(ta.n - g_row0);
-  const size_t col_lo = (MODE == MS_MODE_UPDATE) ? g_row0 : ta.col_lo_panel;
-  double *Ct = ta.C + (size_t)rt * MS_BM * ta.ldc;
+      // -------------------------------------------------------------------- epilogue
+      // lane owns, per (ib, jb, a): row wm*32 + 16*ib + 2p + a, columns wn*32 + 16*jb + 4q .. +3.
+      // One row (= 4 x 16-byte vectors) is loaded as a batch before it is used, so a warp pays one
+      // memory round trip per row instead of one per vector.
 #pragma unroll
-  for (int ib = 0; ib < 2; ib++)
+      for (int ib = 0; ib < 2; ib++)
 #pragma unroll
-    for (int a = 0; a < 2; a++)
-      {
-        const int r = wm * 32 + 16 * ib + 2 * p + a;
-        if (r >= rows_valid)
-          continue;
-        double *crow = Ct + (size_t)r * ta.ldc;
-#pragma unroll
-        for (int jb = 0; jb < 2; jb++)
+        for (int a = 0; a < 2; a++)
           {
-            const size_t cc = col0 + wn * 32 + 16 * jb + 4 * q;
-            double v[4] = {acc[ib][jb][a][0][0], acc[ib][jb][a][1][0], acc[ib][jb][a][0][1],
-                           acc[ib][jb][a][1][1]};
-            if (cc >= col_lo && cc + 3 < ta.n)
+            const int r = wm * 32 + 16 * ib + 2 * p + a;
+            if (r >= rows_valid)
+              continue;
+            double *crow = Ct + (size_t)r * ta.ldc;
+            const size_t cbase = col0 + wn * 32 + 4 * q;
+            double v[2][4];
+#pragma unroll
+            for (int jb = 0; jb < 2; jb++)
               {
-                double2 *ptr = reinterpret_cast<double2 *> (crow + cc);
+                v[jb][0] = acc[ib][jb][a][0][0];
+                v[jb][1] = acc[ib][jb][a][1][0];
+                v[jb][2] = acc[ib][jb][a][0][1];
+                v[jb][3] = acc[ib][jb][a][1][1];
+              }
+            const bool fast0 = cbase >= col_lo && cbase + 3 < ta.n;
+            const bool fast1 = cbase + 16 >= col_lo && cbase + 19 < ta.n;
+            if (fast0 && fast1)
+              {
+                double2 *p0 = reinterpret_cast<double2 *> (crow + cbase);
+                double2 *p1 = reinterpret_cast<double2 *> (crow + cbase + 16);
                 if (MODE == MS_MODE_UPDATE)
                   {
-                    double2 o0 = ptr[0], o1 = ptr[1];
-                    o0.x -= v[0];
-                    o0.y -= v[1];
-                    o1.x -= v[2];
-                    o1.y -= v[3];
-                    ptr[0] = o0;
-                    ptr[1] = o1;
+                    double2 o00 = p0[0], o01 = p0[1], o10 = p1[0], o11 = p1[1];
+                    o00.x -= v[0][0];
+                    o00.y -= v[0][1];
+                    o01.x -= v[0][2];
+                    o01.y -= v[0][3];
+                    o10.x -= v[1][0];
+                    o10.y -= v[1][1];
+                    o11.x -= v[1][2];
+                    o11.y -= v[1][3];
+                    p0[0] = o00;
+                    p0[1] = o01;
+                    p1[0] = o10;
+                    p1[1] = o11;
                   }
                 else
                   {
-                    ptr[0] = make_double2 (v[0], v[1]);
-                    ptr[1] = make_double2 (v[2], v[3]);
-                    double2 *p2 = reinterpret_cast<double2 *> (
-                        ta.C2 + chunk_major_index (ta.c2_k0 + r, cc, ta.c2_H));
-                    p2[0] = make_double2 (v[0], v[1]);
-                    p2[1] = make_double2 (v[2], v[3]);
+                    p0[0] = make_double2 (v[0][0], v[0][1]);
+                    p0[1] = make_double2 (v[0][2], v[0][3]);
+                    p1[0] = make_double2 (v[1][0], v[1][1]);
+                    p1[1] = make_double2 (v[1][2], v[1][3]);
+                    double2 *q0 = reinterpret_cast<double2 *> (ta.C2 + chunk_major_index (ta.c2_k0 + r, cbase, ta.c2_H));
+                    double2 *q1 = reinterpret_cast<double2 *> (ta.C2 + chunk_major_index (ta.c2_k0 + r, cbase + 16, ta.c2_H));
+                    q0[0] = make_double2 (v[0][0], v[0][1]);
+                    q0[1] = make_double2 (v[0][2], v[0][3]);
+                    q1[0] = make_double2 (v[1][0], v[1][1]);
+                    q1[1] = make_double2 (v[1][2], v[1][3]);
                   }
               }
             else
               {
 #pragma unroll
-                for (int t = 0; t < 4; t++)
-                  {
-                    const size_t col = cc + t;
-                    if (col >= col_lo && col < ta.n)
-                      {
-                        if (MODE == MS_MODE_UPDATE)
-                          crow[col] -= v[t];
-                        else
-                          {
-                            crow[col] = v[t];
-                            ta.C2[chunk_major_index (ta.c2_k0 + r, col, ta.c2_H)] = v[t];
-                          }
-                      }
-                  }
+                for (int jb = 0; jb < 2; jb++)
+#pragma unroll
+                  for (int tt = 0; tt < 4; tt++)
+                    {
+                      const size_t col = cbase + 16 * jb + tt;
+                      if (col >= col_lo && col < ta.n)
+                        {
+                          if (MODE == MS_MODE_UPDATE)
+                            crow[col] -= v[jb][tt];
+                          else
+                            {
+                              crow[col] = v[jb][tt];
+                              ta.C2[chunk_major_index (ta.c2_k0 + r, col, ta.c2_H)] = v[jb][tt];
+                            }
+                        }
+                    }
               }
           }
-      }
+    }
 }
 
 // ---------------------------------------------------------------------------- tensor maps
@@ -315,6 +429,29 @@ ms_tile_setup (ms_ctx *c)
   return MS_OK;
 }
 
+static int
+tile_total (const tile_args &ta, int mode)
+{
+  long long total = 0;
+  for (int rt = 0; rt < ta.n_row_tiles; rt++)
+    total += tile_count_in_row (ta, mode, rt);
+  return (int)std::min<long long> (total, 0x7fffffff);
+}
+
+// At least ~8 waves of CTAs (2 per SM) so that the tail stays small; at most MS_TILES_PER_CTA.
+static int g_tiles_per_cta_max = -1;
+static int
+tiles_per_cta_for (const ms_ctx *c, int total)
+{
+  if (g_tiles_per_cta_max < 0)
+    {
+      const char *e = getenv ("MS_TILES_PER_CTA");
+      g_tiles_per_cta_max = e ? std::max (1, atoi (e)) : 4;
+    }
+  int t = total / (2 * c->sm_count * 8);
+  return std::max (1, std::min (t, g_tiles_per_cta_max));
+}
+
 // Update local rows [lrow_begin, lrow_end) (64-row tiles of block rows J > I, or the later pieces
 // of block row I itself) with rows [k0, k0+K) of panel buffer `pb` (= factored block row I).
 int
@@ -324,34 +461,35 @@ ms_k_tile_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_en
   if (lrow_end <= lrow_begin)
     return MS_OK;
   MS_CHECK_ARG (c->have_tm, "tile kernel not set up");
-  MS_CHECK_ARG (K % MS_KC == 0 && K <= TILE_MAX_K, "K must be a multiple of 16 and <= 2048");
+  MS_CHECK_ARG (K % MS_KC == 0 && K <= TILE_MAX_K, "K must be a multiple of 16 and <= 1024");
   MS_CHECK_ARG (lrow_begin % MS_BM == 0, "row range must start on a tile boundary");
-  size_t lb = lrow_begin / c->m;
-  size_t g0 = (lb * (size_t)c->nranks + (size_t)c->rank) * c->m + (lrow_begin - lb * c->m);
-  if (g0 >= c->n)
-    return MS_OK;
-  tile_args ta = {};
-  ta.ax0 = 0; ta.axs = 0; ta.ay0 = (int)k0; ta.ays = (int)c->hpb;
-  ta.bx0 = 0; ta.bxs = 0; ta.by0 = (int)k0; ta.bys = (int)c->hpb;
-  ta.K = K;
-  ta.dsign = c->vec[MS_VEC_D] + I * c->m + k0;
-  ta.C = c->A + lrow_begin * c->ld;
-  ta.ldc = c->ld;
-  ta.C2 = nullptr;
-  ta.lrow_begin = lrow_begin;
-  ta.m = c->m;
-  ta.rank = c->rank;
-  ta.nranks = c->nranks;
-  ta.g0 = g0;
-  ta.col_tile0 = g0 / MS_BN;
-  ta.n = c->n;
-  size_t col_tiles = (c->n + MS_BN - 1) / MS_BN - ta.col_tile0;
-  size_t row_tiles = (lrow_end - lrow_begin + MS_BM - 1) / MS_BM;
-  dim3 grid ((unsigned)col_tiles, (unsigned)row_tiles);
-  tile_dmma_kernel<MS_MODE_UPDATE><<<grid, MS_TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_PB[pb], c->tm_PB[pb], ta);
-  LAUNCH_COUNT (c);
-  c->stats.update_launches++;
-  c->stats.used_dmma = 1;
+  for (size_t lr = lrow_begin; lr < lrow_end; lr += (size_t)TILE_MAX_RT * MS_BM)
+    {
+      size_t lr_end = std::min (lrow_end, lr + (size_t)TILE_MAX_RT * MS_BM);
+      tile_args ta = {};
+      ta.ax0 = 0; ta.axs = 0; ta.ay0 = (int)k0; ta.ays = (int)c->hpb;
+      ta.bx0 = 0; ta.bxs = 0; ta.by0 = (int)k0; ta.bys = (int)c->hpb;
+      ta.K = K;
+      ta.dsign = c->vec[MS_VEC_D] + I * c->m + k0;
+      ta.C = c->A + lr * c->ld;
+      ta.ldc = c->ld;
+      ta.C2 = nullptr;
+      ta.lrow_begin = lr;
+      ta.m = c->m;
+      ta.rank = c->rank;
+      ta.nranks = c->nranks;
+      ta.n_row_tiles = (int)((lr_end - lr + MS_BM - 1) / MS_BM);
+      ta.n = c->n;
+      int total = tile_total (ta, MS_MODE_UPDATE);
+      if (total == 0)
+        continue;
+      ta.tiles_per_cta = tiles_per_cta_for (c, total);
+      unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
+      tile_dmma_kernel<MS_MODE_UPDATE><<<grid, MS_TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_PB[pb], c->tm_PB[pb], ta);
+      LAUNCH_COUNT (c);
+      c->stats.update_launches++;
+      c->stats.used_dmma = 1;
+    }
   MS_CUDA (cudaGetLastError ());
   return MS_OK;
 }
@@ -378,12 +516,16 @@ ms_k_tile_panel (ms_ctx *c, int pb, const ms_piece &pc, size_t I, cudaStream_t s
   ta.m = c->m;
   ta.rank = c->rank;
   ta.nranks = c->nranks;
+  ta.n_row_tiles = 1;
   ta.g0 = pc.row0;
   ta.col_tile0 = col_lo / MS_BN;
   ta.col_lo_panel = col_lo;
   ta.n = c->n;
-  size_t col_tiles = (c->n + MS_BN - 1) / MS_BN - ta.col_tile0;
-  dim3 grid ((unsigned)col_tiles, 1);
+  int total = tile_total (ta, MS_MODE_PANEL);
+  if (total == 0)
+    return MS_OK;
+  ta.tiles_per_cta = tiles_per_cta_for (c, total);
+  unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
   tile_dmma_kernel<MS_MODE_PANEL><<<grid, MS_TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, ta);
   LAUNCH_COUNT (c);
   MS_CUDA (cudaGetLastError ());
