@@ -5,7 +5,7 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 CXX ?= g++
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v $(EXTRA_NVFLAGS)
 CSRC := matrix_solver_b200/csrc
 HOST := matrix_solver_b200/host
 LIBDIR := matrix_solver_b200/lib

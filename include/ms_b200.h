@@ -124,6 +124,9 @@ int ms_block_upper_inverse (const double *a_packed, double *inv_packed, int w,
 /* DRtA / DRtA_l, src/matrix_op.cpp:287-368: A(h x w) <- D inv^T A */
 int ms_block_panel (const double *inv_packed, double *A, const double *D, int h,
                     int w);
+/* the same quantity from the FACTOR itself (what the factorisation's panel step runs):
+ * A(h x w) <- D R^{-T} A by a triangular solve, R packed upper, h <= 64 */
+int ms_block_trsm_panel (const double *r_packed, double *A, const double *D, int h, int w);
 /* minus_RTDR_o1 / minus_RTDR_l_o1, src/matrix_op.cpp:4-39,156-222:
  * A(h x w) -= R1(k x h)^T diag(D) R2(k x w) */
 int ms_block_update (double *A, const double *R1, const double *D, const double *R2,

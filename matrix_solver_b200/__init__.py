@@ -13,6 +13,7 @@ from .capi import (  # noqa: F401
     Solver,
     block_diag_factor,
     block_panel,
+    block_trsm_panel,
     block_update,
     block_update_diag,
     block_upper_inverse,

@@ -75,6 +75,7 @@ def load():
         "ms_block_diag_factor": (ci, [dp, dp, ci, cd]),
         "ms_block_upper_inverse": (ci, [dp, dp, ci, cd]),
         "ms_block_panel": (ci, [dp, dp, dp, ci, ci]),
+        "ms_block_trsm_panel": (ci, [dp, dp, dp, ci, ci]),
         "ms_block_update": (ci, [dp, dp, dp, dp, ci, ci, ci]),
         "ms_block_update_diag": (ci, [dp, dp, dp, ci, ci]),
         "ms_norm2": (ci, [dp, sz, C.POINTER(cd)]),
@@ -96,7 +97,7 @@ EXPORTED = [
     "ms_download_rows", "ms_host_alloc", "ms_host_free", "ms_upload_packed", "ms_download_packed", "ms_get_row", "ms_get_col", "ms_b_and_norm",
     "ms_factor", "ms_solve_forward", "ms_solve_backward", "ms_residual", "ms_set_vec",
     "ms_get_vec", "ms_block_diag_factor", "ms_block_upper_inverse", "ms_block_panel",
-    "ms_block_update", "ms_block_update_diag", "ms_norm2", "ms_error_vs_planted",
+    "ms_block_trsm_panel", "ms_block_update", "ms_block_update_diag", "ms_norm2", "ms_error_vs_planted",
     "ms_probe_dmma_peak", "ms_probe_hbm_copy",
 ]
 
@@ -272,6 +273,13 @@ def block_panel(inv, A, D):
     A = np.ascontiguousarray(A, dtype=np.float64).copy()
     h, w = A.shape
     _check(load().ms_block_panel(_p(_pack(inv)), _p(A), _p(np.ascontiguousarray(D, dtype=np.float64)), h, w))
+    return A
+
+
+def block_trsm_panel(R, A, D):
+    A = np.ascontiguousarray(A, dtype=np.float64).copy()
+    h, w = A.shape
+    _check(load().ms_block_trsm_panel(_p(_pack(R)), _p(A), _p(np.ascontiguousarray(D, dtype=np.float64)), h, w))
     return A
 
 

@@ -241,6 +241,9 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   const char *e = getenv ("MS_FORCE_GENERIC");
   if (e && atoi (e))
     c->force_generic = true;
+  e = getenv ("MS_PANEL_GEMM");
+  if (e && atoi (e))
+    c->panel_trsm = false;
   e = getenv ("MS_NO_LOOKAHEAD");
   if (e && atoi (e))
     c->lookahead = false;
@@ -264,6 +267,8 @@ ms_set_option (ms_ctx *c, const char *key, long value)
     c->lookahead = value != 0;
   else if (!strcmp (key, "profile_update"))
     c->profile_update = value != 0;
+  else if (!strcmp (key, "panel_trsm"))
+    c->panel_trsm = value != 0;
   else
     {
       ms_set_error ("unknown option %s", key);
@@ -657,22 +662,36 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s)
     {
       const ms_piece &pc = c->pieces[pi];
       double *blk = c->A + pc.lrow0 * c->ld + pc.row0;
-      MS_TRY (ms_k_diag (c, blk, c->ld, pc.h, thresh, c->vec[MS_VEC_D] + pc.row0, c->Wt, nullptr, s));
+      double *rows = c->A + pc.lrow0 * c->ld;
       size_t col_lo = pc.row0 + (size_t)pc.h;
-      if (col_lo >= c->n)
-        continue;
       size_t k0 = pc.row0 - I * c->m;
-      if (c->fast && !c->force_generic && pc.h == MS_SUB)
-        MS_TRY (ms_k_tile_panel (c, pb, pc, I, s));
+      const bool tiles = c->fast && !c->force_generic;
+      if (c->panel_trsm)
+        {
+          // K1 then K3 as a triangular solve: no explicit inverse on the critical path
+          MS_TRY (ms_k_diag (c, blk, c->ld, pc.h, thresh, c->vec[MS_VEC_D] + pc.row0, nullptr, nullptr, s));
+          if (col_lo >= c->n)
+            continue;
+          MS_TRY (ms_k_trsm_panel (c, blk, c->ld, rows, c->ld, pc.h, col_lo, c->n, c->vec[MS_VEC_D] + pc.row0,
+                                   c->PB[pb], c->hpb, k0, s));
+        }
       else
         {
-          ms_operand W;
-          W.p = c->Wt;
-          W.ld = 0;
-          W.H = MS_SUB;
-          double *rows = c->A + pc.lrow0 * c->ld;
-          MS_TRY (ms_k_generic_panel (c, W, rows, c->ld, rows, c->ld, pc.h, col_lo, c->PB[pb], c->hpb, k0,
-                                      c->n, s));
+          // the reference's formulation: K1 + K2 (inverse) then K3 = (V D)^T * rows
+          MS_TRY (ms_k_diag (c, blk, c->ld, pc.h, thresh, c->vec[MS_VEC_D] + pc.row0, c->Wt, nullptr, s));
+          if (col_lo >= c->n)
+            continue;
+          if (tiles && pc.h == MS_SUB)
+            MS_TRY (ms_k_tile_panel (c, pb, pc, I, s));
+          else
+            {
+              ms_operand W;
+              W.p = c->Wt;
+              W.ld = 0;
+              W.H = MS_SUB;
+              MS_TRY (ms_k_generic_panel (c, W, rows, c->ld, rows, c->ld, pc.h, col_lo, c->PB[pb], c->hpb, k0,
+                                          c->n, s));
+            }
         }
       // later pieces of the same block row
       size_t lr_next = pc.lrow0 + (size_t)pc.h;
@@ -1095,6 +1114,30 @@ ms_block_panel (const double *inv_packed, double *A, const double *D, int h, int
   return MS_OK;
 }
 
+extern "C" int
+ms_block_trsm_panel (const double *r_packed, double *A, const double *D, int h, int w)
+{
+  MS_CHECK_ARG (r_packed && A && D && h >= 1 && h <= MS_SUB && w >= 1, "bad argument (1 <= h <= 64)");
+  ms_ctx *c;
+  MS_TRY (blk_ctx (&c));
+  std::vector<double> R ((size_t)h * h);
+  unpack_upper (r_packed, R.data (), h);
+  dev_buf dR, dA, dD, dPB;
+  size_t ldw = round_up ((size_t)w, MS_CHUNK);
+  MS_TRY (dR.alloc ((size_t)h * h));
+  MS_TRY (dA.alloc ((size_t)h * w));
+  MS_TRY (dD.alloc (h));
+  MS_TRY (dPB.alloc (ldw * MS_SUB));
+  cudaStream_t s = c->s_main;
+  MS_CUDA (cudaMemcpyAsync (dR.p, R.data (), R.size () * 8, cudaMemcpyHostToDevice, s));
+  MS_CUDA (cudaMemcpyAsync (dA.p, A, (size_t)h * w * 8, cudaMemcpyHostToDevice, s));
+  MS_CUDA (cudaMemcpyAsync (dD.p, D, h * 8, cudaMemcpyHostToDevice, s));
+  MS_TRY (ms_k_trsm_panel (c, dR.p, (size_t)h, dA.p, (size_t)w, h, 0, (size_t)w, dD.p, dPB.p, MS_SUB, 0, s));
+  MS_CUDA (cudaMemcpyAsync (A, dA.p, (size_t)h * w * 8, cudaMemcpyDeviceToHost, s));
+  MS_CUDA (cudaStreamSynchronize (s));
+  return MS_OK;
+}
+
 static int
 block_update_common (double *A_full, size_t a_cnt, const double *R1, const double *D, const double *R2, int k,
                      int h, int w, int upper_only)
@@ -1169,5 +1212,15 @@ ms_error_vs_planted (const double *x, size_t n, double *out)
   double o[2];
   MS_TRY (vec_norms (nullptr, x, n, o));
   *out = sqrt (o[1]);
+  return MS_OK;
+}
+
+// debug hook (not part of the public header): raw flag words of the block-API context
+extern "C" int
+ms_debug_blk_flags (int *out8)
+{
+  ms_ctx *c;
+  MS_TRY (blk_ctx (&c));
+  MS_CUDA (cudaMemcpy (out8, c->flags, 8 * sizeof (int), cudaMemcpyDeviceToHost));
   return MS_OK;
 }

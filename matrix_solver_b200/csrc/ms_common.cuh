@@ -87,6 +87,7 @@ struct ms_ctx
   bool force_generic = false;
   bool lookahead = true;
   bool profile_update = false;
+  bool panel_trsm = true;   // K3 as a triangular solve (default) or as a DMMA product with the inverse
 
   double *A = nullptr;       // rows_alloc x ld, row-major; only j >= i meaningful
   double *PB[2] = {nullptr, nullptr};  // panel buffers, chunk-major [ld/16][hpb][16]
@@ -248,6 +249,9 @@ int ms_k_axpy_minus (ms_ctx *c, double *r, const double *b, size_t n, cudaStream
 int ms_k_pretest (ms_ctx *c, const double *blk, size_t ld, int h, double thresh, cudaStream_t s);
 int ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_out,
                double *wt_out, double *inv_out, cudaStream_t s);
+int ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t ld, int h, size_t col_lo,
+                     size_t n, const double *dpiece, double *PB, size_t pb_H, size_t pb_k0,
+                     cudaStream_t s);
 
 // ms_kernels_tile.cu
 int ms_tile_setup (ms_ctx *c);

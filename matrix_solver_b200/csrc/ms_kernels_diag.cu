@@ -41,9 +41,15 @@ ms_k_pretest (ms_ctx *c, const double *blk, size_t ld, int h, double thresh, cud
 }
 
 // dynamic smem: a[h][h+1] | v[h][h+1] | rdiag[h] | dd[h]
+// 256 threads as a 16 x 16 grid (tx fastest): all loops over the block are 2-D strided, no integer
+// divisions.  NT = ceil(hmax / 16) bounds the per-thread patch of the trailing update so that its
+// operands can be gathered into registers first (loads pipeline, then the independent
+// multiply-multiply-subtract chains pipeline) instead of one load-compute-store round trip per entry.
+template <int NT>
 __global__ void __launch_bounds__ (256)
 diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *__restrict__ d_out,
-             double *__restrict__ wt_out, int wt_h, double *__restrict__ inv_out, int *flags)
+             double *__restrict__ wt_out, int wt_h, double *__restrict__ inv_out, int want_inverse,
+             int *flags)
 {
   extern __shared__ double smd[];
   const int S = h + 1;
@@ -52,18 +58,23 @@ diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *
   double *rdiag = v + (size_t)h * S;
   double *dd = rdiag + h;
   const int tid = threadIdx.x;
-
-  for (int e = tid; e < h * h; e += 256)
-    {
-      int i = e / h, j = e - i * h;
-      a[i * S + j] = j >= i ? blk[(size_t)i * ld + j] : 0.0;
-      v[i * S + j] = 0.0;
-    }
-  __syncthreads ();
-
-  // ---- K1: signed Cholesky, right-looking inside the piece (16 x 16 thread grid over the
-  // trailing square; no integer divisions on the critical path)
   const int tx = tid & 15, ty = tid >> 4;
+#ifdef MS_DIAG_TIMING
+  long long tc0 = clock64 ();
+#endif
+
+  for (int i = ty; i < h; i += 16)
+    for (int j = tx; j < h; j += 16)
+      {
+        a[i * S + j] = j >= i ? blk[(size_t)i * ld + j] : 0.0;
+        v[i * S + j] = 0.0;
+      }
+  __syncthreads ();
+#ifdef MS_DIAG_TIMING
+  long long tc1 = clock64 ();
+#endif
+
+  // ---- K1: signed Cholesky, right-looking inside the piece
   for (int i = 0; i < h; i++)
     {
       double s = a[i * S + i];
@@ -80,77 +91,205 @@ diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *
       for (int j = i + 1 + tid; j < h; j += 256)
         a[i * S + j] = __ddiv_rn (a[i * S + j], den);
       __syncthreads ();
-      for (int k = i + 1 + ty; k < h; k += 16)
+      // trailing square (rows k > i, cols j >= k): gather, compute, scatter
+      double rk[NT], rj[NT], c[NT][NT];
+#pragma unroll
+      for (int u = 0; u < NT; u++)
         {
-          const double aik = a[i * S + k];
-          for (int j = i + 1 + tx; j < h; j += 16)
-            if (j >= k)
-              a[k * S + j] = __dsub_rn (a[k * S + j], __dmul_rn (__dmul_rn (aik, a[i * S + j]), di));
+          const int k = i + 1 + ty + 16 * u, j = i + 1 + tx + 16 * u;
+          rk[u] = k < h ? a[i * S + k] : 0.0;
+          rj[u] = j < h ? a[i * S + j] : 0.0;
+        }
+#pragma unroll
+      for (int u = 0; u < NT; u++)
+#pragma unroll
+        for (int w = 0; w < NT; w++)
+          {
+            const int k = i + 1 + ty + 16 * u, j = i + 1 + tx + 16 * w;
+            c[u][w] = (k < h && j < h && j >= k) ? a[k * S + j] : 0.0;
+          }
+#pragma unroll
+      for (int u = 0; u < NT; u++)
+#pragma unroll
+        for (int w = 0; w < NT; w++)
+          c[u][w] = __dsub_rn (c[u][w], __dmul_rn (__dmul_rn (rk[u], rj[w]), di));
+#pragma unroll
+      for (int u = 0; u < NT; u++)
+#pragma unroll
+        for (int w = 0; w < NT; w++)
+          {
+            const int k = i + 1 + ty + 16 * u, j = i + 1 + tx + 16 * w;
+            if (k < h && j < h && j >= k)
+              a[k * S + j] = c[u][w];
+          }
+      __syncthreads ();
+    }
+#ifdef MS_DIAG_TIMING
+  long long tc2 = clock64 ();
+#endif
+
+  // ---- K2: inverse, one thread per column, rows bottom-up, k ascending
+  if (want_inverse)
+    {
+      for (int j = tid; j < h; j += 256)
+        {
+          for (int i = j; i >= 0; i--)
+            {
+              double val;
+              if (i == j)
+                val = __ddiv_rn (1.0, rdiag[i]);
+              else
+                {
+                  double sum = 0;
+                  for (int k = i + 1; k <= j; k++)
+                    sum = __dadd_rn (sum, __dmul_rn (a[i * S + k], v[k * S + j]));
+                  val = __ddiv_rn (-sum, rdiag[i]);
+                }
+              v[i * S + j] = val;
+            }
         }
       __syncthreads ();
     }
-
-  // ---- K2: inverse, one thread per column, rows bottom-up, k ascending
-  for (int j = tid; j < h; j += 256)
-    {
-      for (int i = j; i >= 0; i--)
-        {
-          double val;
-          if (i == j)
-            val = __ddiv_rn (1.0, rdiag[i]);
-          else
-            {
-              double sum = 0;
-              for (int k = i + 1; k <= j; k++)
-                sum = __dadd_rn (sum, __dmul_rn (a[i * S + k], v[k * S + j]));
-              val = __ddiv_rn (-sum, rdiag[i]);
-            }
-          v[i * S + j] = val;
-        }
-    }
-  __syncthreads ();
+#ifdef MS_DIAG_TIMING
+  long long tc3 = clock64 ();
+#endif
 
   // ---- write back: R in place (upper), d, the inverse, and Wt = inverse * D (chunk-major)
-  for (int e = tid; e < h * h; e += 256)
-    {
-      int i = e / h, j = e - i * h;
-      if (j > i)
-        blk[(size_t)i * ld + j] = a[i * S + j];
-      else if (j == i)
-        blk[(size_t)i * ld + j] = rdiag[i];
-    }
+  for (int i = ty; i < h; i += 16)
+    for (int j = tx; j < h; j += 16)
+      {
+        if (j > i)
+          blk[(size_t)i * ld + j] = a[i * S + j];
+        else if (j == i)
+          blk[(size_t)i * ld + j] = rdiag[i];
+        if (inv_out)
+          inv_out[(size_t)i * h + j] = j >= i ? v[i * S + j] : 0.0;
+      }
   if (d_out)
     for (int i = tid; i < h; i += 256)
       d_out[i] = dd[i];
-  if (inv_out)
-    for (int e = tid; e < h * h; e += 256)
-      {
-        int i = e / h, j = e - i * h;
-        inv_out[(size_t)i * h + j] = j >= i ? v[i * S + j] : 0.0;
-      }
   if (wt_out)
-    for (int e = tid; e < wt_h * wt_h; e += 256)
-      {
-        int k = e / wt_h, i = e - k * wt_h;
-        double val = (k < h && i < h && i >= k) ? v[k * S + i] * dd[i] : 0.0;
-        wt_out[chunk_major_index (k, i, wt_h)] = val;
-      }
+    for (int k = ty; k < wt_h; k += 16)
+      for (int i = tx; i < wt_h; i += 16)
+        {
+          double val = (k < h && i < h && i >= k) ? v[k * S + i] * dd[i] : 0.0;
+          wt_out[chunk_major_index (k, i, wt_h)] = val;
+        }
+#ifdef MS_DIAG_TIMING
+  __syncthreads ();
+  if (tid == 0)
+    {
+      long long tc4 = clock64 ();
+      flags[4] = (int)(tc1 - tc0);
+      flags[5] = (int)(tc2 - tc1);
+      flags[6] = (int)(tc3 - tc2);
+      flags[7] = (int)(tc4 - tc3);
+    }
+#endif
 }
 
-// d_out: h doubles (device), wt_out: chunk-major [MS_SUB/16][MS_SUB][16] or null
+// d_out: h doubles (device), wt_out: chunk-major [MS_SUB/16][MS_SUB][16] or null.  The inverse is
+// computed only when someone consumes it (wt_out / inv_out).
 int
 ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_out, double *wt_out,
            double *inv_out, cudaStream_t s)
 {
   MS_CHECK_ARG (h >= 1 && h <= 112, "diag piece must have 1..112 rows");
   size_t smem = (2 * (size_t)h * (h + 1) + 2 * h) * sizeof (double);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured)
+  static bool configured = false;
+  if (!configured)
     {
-      MS_CUDA (cudaFuncSetAttribute (diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      configured = 227 * 1024;
+      MS_CUDA (cudaFuncSetAttribute (diag_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      MS_CUDA (cudaFuncSetAttribute (diag_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      configured = true;
     }
-  diag_kernel<<<1, 256, smem, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, c->flags);
+  int want_inverse = (wt_out != nullptr || inv_out != nullptr);
+  if (h <= 64)
+    diag_kernel<4><<<1, 256, smem, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse, c->flags);
+  else
+    diag_kernel<7><<<1, 256, smem, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse, c->flags);
+  LAUNCH_COUNT (c);
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
+// ============================================================================ TRSM panel (K3)
+// X = D * R^{-T} * A for the h rows of one piece and the columns [col_lo, n), in place, plus a copy
+// into the panel buffer.  This is what DRtA / DRtA_l (src/matrix_op.cpp:287-368) compute with the
+// explicit inverse; here it is a true triangular solve, one thread per column:
+//     x_i = (a_i - sum_{k<i} R_ki x_k) / R_ii,   row i then scaled by d_i.
+// R (64 x 64, upper) is staged in shared memory and read with 16-byte broadcast loads; each thread
+// keeps its column in registers (right-looking: after x_i, rows k > i lose R_ik x_i — 63 independent
+// FMAs, so the kernel runs at DFMA issue rate).  Loads/stores are coalesced across the warp (adjacent
+// threads = adjacent columns): 16 B of HBM traffic per element + 8 B for the panel-buffer copy.
+__global__ void __launch_bounds__ (128, 3)
+trsm_panel_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restrict__ rows, size_t ld, int h, size_t col_lo,
+                   size_t n, const double *__restrict__ dpiece, double *__restrict__ PB, size_t pb_H, size_t pb_k0)
+{
+  // RT[i][k] = R(k, i) for k < i (the column of R that row i of the solve needs), 0 elsewhere
+  constexpr int RS = MS_SUB + 2;  // row stride: even (16-byte loads) and not a multiple of 32 banks
+  __shared__ __align__ (16) double RT[MS_SUB * RS];
+  __shared__ double rinv[MS_SUB], ds[MS_SUB];
+  for (int e = threadIdx.x; e < MS_SUB * MS_SUB; e += 128)
+    {
+      const int k = e >> 6, i = e & 63;  // coalesced read of row k of R
+      RT[i * RS + k] = (i < h && k < i) ? Rblk[(size_t)k * ldr + i] : 0.0;
+    }
+  if (threadIdx.x < MS_SUB)
+    {
+      const int i = threadIdx.x;
+      rinv[i] = i < h ? 1.0 / Rblk[(size_t)i * ldr + i] : 1.0;
+      ds[i] = i < h ? dpiece[i] : 1.0;
+    }
+  __syncthreads ();
+  const size_t j = col_lo + (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (j >= n)
+    return;
+  double x[MS_SUB];
+  double *pcol = rows + j;
+  double *ppb = PB + chunk_major_index (pb_k0, j, pb_H);
+  double a_next = rows[j];
+#pragma unroll
+  for (int i = 0; i < MS_SUB; i++)
+    {
+      const double a_i = a_next;
+      if (i + 1 < MS_SUB)
+        a_next = (i + 1 < h) ? pcol[(size_t)(i + 1) * ld] : 0.0;  // prefetch the next row's entry
+      // four interleaved partial sums keep four independent FMA chains in flight
+      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < (i & ~3); k += 4)
+        {
+          const double2 ra = *reinterpret_cast<const double2 *> (&RT[i * RS + k]);
+          const double2 rb = *reinterpret_cast<const double2 *> (&RT[i * RS + k + 2]);
+          p0 = fma (ra.x, x[k], p0);
+          p1 = fma (ra.y, x[k + 1], p1);
+          p2 = fma (rb.x, x[k + 2], p2);
+          p3 = fma (rb.y, x[k + 3], p3);
+        }
+#pragma unroll
+      for (int k = (i & ~3); k < i; k++)
+        p0 = fma (RT[i * RS + k], x[k], p0);
+      const double xi = (a_i - ((p0 + p1) + (p2 + p3))) * rinv[i];
+      x[i] = xi;
+      if (i < h)
+        {
+          const double val = xi * ds[i];
+          pcol[(size_t)i * ld] = val;
+          ppb[(size_t)i * MS_CHUNK] = val;   // next k row of the same 16-column chunk
+        }
+    }
+}
+
+int
+ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t ld, int h, size_t col_lo, size_t n,
+                 const double *dpiece, double *PB, size_t pb_H, size_t pb_k0, cudaStream_t s)
+{
+  if (col_lo >= n)
+    return MS_OK;
+  MS_CHECK_ARG (h >= 1 && h <= MS_SUB, "trsm panel piece must have 1..64 rows");
+  unsigned grid = (unsigned)((n - col_lo + 127) / 128);
+  trsm_panel_kernel<<<grid, 128, 0, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H, pb_k0);
   LAUNCH_COUNT (c);
   MS_CUDA (cudaGetLastError ());
   return MS_OK;

@@ -162,6 +162,22 @@ def test_block_update_and_panel(ms, ora, k, h, w):
     assert np.all(np.abs(got - want) <= 4 * k * EPS * scale)
 
 
+@pytest.mark.parametrize("h,w", [(1, 1), (3, 5), (17, 40), (64, 64), (64, 300), (50, 129)])
+def test_block_trsm_panel_matches_inverse_formulation(ms, ora, h, w):
+    """The factorisation's panel step is a triangular solve; the reference forms the explicit inverse
+    and multiplies (reverse_upper + DRtA).  Same quantity, compared with a cond(R)-scaled bound."""
+    rng = np.random.default_rng(h * 100 + w)
+    R = np.triu(rng.standard_normal((h, h)) * 0.3) + np.diag(1.0 + rng.random(h))
+    A = rng.standard_normal((h, w))
+    D = np.where(rng.random(h) < 0.3, -1.0, 1.0)
+    inv, fail = ora.upper_inverse(R, 1.0)
+    assert not fail
+    want = ora.panel(np.triu(inv), A, D)
+    got = ms.block_trsm_panel(R, A, D)
+    bound = 8 * h * EPS * (np.abs(np.triu(inv)).T @ np.abs(R).T @ np.abs(np.triu(inv)).T @ np.abs(A))
+    assert np.all(np.abs(got - want) <= bound + 1e-300)
+
+
 def test_vector_norms(ms, ora):
     rng = np.random.default_rng(5)
     for n in (1, 2, 7, 1000, 4097):
@@ -212,7 +228,8 @@ def test_pipeline_against_oracle_formula_sweep(ms, ora, n, m):
     assert o["stats"]["used_dmma"] == (1 if (m % 64 == 0 and n > 64) else 0)
 
 
-@pytest.mark.parametrize("opts", [(("force_generic", 1),), (("lookahead", 0),), (("force_generic", 1), ("lookahead", 0))])
+@pytest.mark.parametrize("opts", [(("force_generic", 1),), (("lookahead", 0),), (("force_generic", 1), ("lookahead", 0)),
+                                  (("panel_trsm", 0),), (("panel_trsm", 0), ("force_generic", 1))])
 def test_kernel_families_and_schedules_agree(ms, opts):
     """DMMA tiles vs generic DFMA kernel, look-ahead vs in-order: same factor within rounding."""
     n, m = 640, 128
