@@ -657,10 +657,13 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s)
   const size_t rowsI = c->block_rows (I);
   const size_t lrowI = (I / (size_t)c->nranks) * c->m;
   double *diag0 = c->A + lrowI * c->ld + I * c->m;
-  MS_TRY (ms_k_pretest (c, diag0, c->ld, (int)rowsI, thresh, s));
   for (size_t pi = c->block_first_piece[I]; pi < c->block_first_piece[I + 1]; pi++)
     {
       const ms_piece &pc = c->pieces[pi];
+      // the block row's pre-update pivot test rides along with its first piece's diag kernel
+      const bool first = pi == c->block_first_piece[I];
+      const double *pre = first ? diag0 : nullptr;
+      const int pre_count = first ? (int)rowsI : 0;
       double *blk = c->A + pc.lrow0 * c->ld + pc.row0;
       double *rows = c->A + pc.lrow0 * c->ld;
       size_t col_lo = pc.row0 + (size_t)pc.h;
@@ -669,7 +672,8 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s)
       if (c->panel_trsm)
         {
           // K1 then K3 as a triangular solve: no explicit inverse on the critical path
-          MS_TRY (ms_k_diag (c, blk, c->ld, pc.h, thresh, c->vec[MS_VEC_D] + pc.row0, nullptr, nullptr, s));
+          MS_TRY (ms_k_diag (c, blk, c->ld, pc.h, thresh, c->vec[MS_VEC_D] + pc.row0, nullptr, nullptr, pre, c->ld,
+                             pre_count, s));
           if (col_lo >= c->n)
             continue;
           MS_TRY (ms_k_trsm_panel (c, blk, c->ld, rows, c->ld, pc.h, col_lo, c->n, c->vec[MS_VEC_D] + pc.row0,
@@ -678,7 +682,8 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s)
       else
         {
           // the reference's formulation: K1 + K2 (inverse) then K3 = (V D)^T * rows
-          MS_TRY (ms_k_diag (c, blk, c->ld, pc.h, thresh, c->vec[MS_VEC_D] + pc.row0, c->Wt, nullptr, s));
+          MS_TRY (ms_k_diag (c, blk, c->ld, pc.h, thresh, c->vec[MS_VEC_D] + pc.row0, c->Wt, nullptr, pre, c->ld,
+                             pre_count, s));
           if (col_lo >= c->n)
             continue;
           if (tiles && pc.h == MS_SUB)
@@ -993,8 +998,7 @@ ms_block_diag_factor (double *a_packed, double *d, int w, double norma)
   cudaStream_t s = c->s_main;
   MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), s));
   MS_CUDA (cudaMemcpyAsync (da.p, full.data (), full.size () * 8, cudaMemcpyHostToDevice, s));
-  MS_TRY (ms_k_pretest (c, da.p, w, w, 1.e-14 * norma, s));
-  MS_TRY (ms_k_diag (c, da.p, w, w, 1.e-14 * norma, dd.p, nullptr, nullptr, s));
+  MS_TRY (ms_k_diag (c, da.p, w, w, 1.e-14 * norma, dd.p, nullptr, nullptr, da.p, w, w, s));
   MS_CUDA (cudaMemcpyAsync (full.data (), da.p, full.size () * 8, cudaMemcpyDeviceToHost, s));
   MS_CUDA (cudaMemcpyAsync (d, dd.p, w * 8, cudaMemcpyDeviceToHost, s));
   int flag;

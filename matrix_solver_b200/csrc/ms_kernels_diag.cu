@@ -41,15 +41,20 @@ ms_k_pretest (ms_ctx *c, const double *blk, size_t ld, int h, double thresh, cud
 }
 
 // dynamic smem: a[h][h+1] | v[h][h+1] | rdiag[h] | dd[h]
-// 256 threads as a 16 x 16 grid (tx fastest): all loops over the block are 2-D strided, no integer
-// divisions.  NT = ceil(hmax / 16) bounds the per-thread patch of the trailing update so that its
-// operands can be gathered into registers first (loads pipeline, then the independent
-// multiply-multiply-subtract chains pipeline) instead of one load-compute-store round trip per entry.
-template <int NT>
+//
+// Schedule of K1 (one __syncthreads per pivot instead of two, and the expensive IEEE sqrt/divide of
+// pivot i+1 overlapped with the bulk of update i):
+//   state before step i : row i is final (updated by pivots < i and scaled), rdiag[i], dd[i] known
+//   warp 0  ("pivot warp"): applies pivot i to row i+1 only, then immediately finishes row i+1
+//                           (sign, sqrt, scale) — the critical path of the whole factorisation
+//   warps 1-7             : apply pivot i to rows k >= i+2 (14 x 16 thread grid, operands gathered
+//                           into registers first so that the loads and the fp64 chains pipeline)
+// Every entry still receives its subtractions in ascending pivot order with the same roundings.
+template <int NTR, int NTC>
 __global__ void __launch_bounds__ (256)
 diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *__restrict__ d_out,
              double *__restrict__ wt_out, int wt_h, double *__restrict__ inv_out, int want_inverse,
-             int *flags)
+             const double *__restrict__ pre_diag, size_t pre_ld, int pre_count, int *flags)
 {
   extern __shared__ double smd[];
   const int S = h + 1;
@@ -59,69 +64,117 @@ diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *
   double *dd = rdiag + h;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
+  const int lane = tid & 31;
 #ifdef MS_DIAG_TIMING
   long long tc0 = clock64 ();
 #endif
+
+  // the reference's pre-update pivot test (src/solver.cpp:117) for the whole block row
+  for (int i = tid; i < pre_count; i += 256)
+    if (fabs (pre_diag[(size_t)i * pre_ld + i]) < thresh)
+      flags[0] = 1;
 
   for (int i = ty; i < h; i += 16)
     for (int j = tx; j < h; j += 16)
       {
         a[i * S + j] = j >= i ? blk[(size_t)i * ld + j] : 0.0;
-        v[i * S + j] = 0.0;
+        if (want_inverse)
+          v[i * S + j] = 0.0;
       }
   __syncthreads ();
 #ifdef MS_DIAG_TIMING
   long long tc1 = clock64 ();
 #endif
 
-  // ---- K1: signed Cholesky, right-looking inside the piece
-  for (int i = 0; i < h; i++)
+  // finish row `row`: its entries are fully updated; compute sign / sqrt / scale (one warp)
+  auto finish_row = [&] (int row, double c0, double c1) {
+    // c0 / c1: updated values of columns row+lane / row+lane+32 ... held by this lane
+    const double s = __shfl_sync (0xffffffffu, c0, 0);  // column `row` itself lives in lane 0
+    const double di = s > 0 ? 1.0 : -1.0;
+    const double rii = __dsqrt_rn (fabs (s));
+    const double den = __dmul_rn (rii, di);
+    if (lane == 0)
+      {
+        rdiag[row] = rii;
+        dd[row] = di;
+        if (fabs (rii) < thresh)
+          flags[0] = 1;
+      }
+    const int j0 = row + lane, j1 = row + lane + 32;
+    if (lane > 0 && j0 < h)
+      a[row * S + j0] = __ddiv_rn (c0, den);
+    if (j1 < h)
+      a[row * S + j1] = __ddiv_rn (c1, den);
+    // columns beyond row + 63 (only for h > 64): same treatment, strided
+    for (int j = row + lane + 64; j < h; j += 32)
+      a[row * S + j] = __ddiv_rn (a[row * S + j], den);
+  };
+
+  if (tid < 32)
     {
-      double s = a[i * S + i];
-      double di = s > 0 ? 1.0 : -1.0;
-      double rii = __dsqrt_rn (fabs (s));
-      double den = __dmul_rn (rii, di);
-      if (tid == 0)
+      const int j0 = lane, j1 = lane + 32;
+      finish_row (0, j0 < h ? a[j0] : 0.0, j1 < h ? a[j1] : 0.0);
+    }
+  __syncthreads ();
+
+  for (int i = 0; i + 1 < h; i++)
+    {
+      const double di = dd[i];
+      if (tid < 32)
         {
-          rdiag[i] = rii;
-          dd[i] = di;
-          if (fabs (rii) < thresh)
-            flags[0] = 1;
+          // pivot warp: row i+1 <- row i+1 - (r_{i,i+1} r_{i,j}) d_i, then finish it
+          const int row = i + 1;
+          const double rk = a[i * S + row];
+          const int j0 = row + lane, j1 = row + lane + 32;
+          double c0 = 0.0, c1 = 0.0;
+          if (j0 < h)
+            c0 = __dsub_rn (a[row * S + j0], __dmul_rn (__dmul_rn (rk, a[i * S + j0]), di));
+          if (j1 < h)
+            c1 = __dsub_rn (a[row * S + j1], __dmul_rn (__dmul_rn (rk, a[i * S + j1]), di));
+          for (int j = row + lane + 64; j < h; j += 32)
+            a[row * S + j] = __dsub_rn (a[row * S + j], __dmul_rn (__dmul_rn (rk, a[i * S + j]), di));
+          finish_row (row, c0, c1);
         }
-      for (int j = i + 1 + tid; j < h; j += 256)
-        a[i * S + j] = __ddiv_rn (a[i * S + j], den);
-      __syncthreads ();
-      // trailing square (rows k > i, cols j >= k): gather, compute, scatter
-      double rk[NT], rj[NT], c[NT][NT];
-#pragma unroll
-      for (int u = 0; u < NT; u++)
+      else
         {
-          const int k = i + 1 + ty + 16 * u, j = i + 1 + tx + 16 * u;
-          rk[u] = k < h ? a[i * S + k] : 0.0;
-          rj[u] = j < h ? a[i * S + j] : 0.0;
+          // rows k >= i+2, cols j >= k: gather, compute, scatter (14 x 16 threads)
+          const int t = tid - 32, ux = t & 15, uy = t >> 4;
+          double rk[NTR], rj[NTC], c[NTR][NTC];
+#pragma unroll
+          for (int u = 0; u < NTR; u++)
+            {
+              const int k = i + 2 + uy + 14 * u;
+              rk[u] = k < h ? a[i * S + k] : 0.0;
+            }
+#pragma unroll
+          for (int w = 0; w < NTC; w++)
+            {
+              const int j = i + 2 + ux + 16 * w;
+              rj[w] = j < h ? a[i * S + j] : 0.0;
+            }
+#pragma unroll
+          for (int u = 0; u < NTR; u++)
+#pragma unroll
+            for (int w = 0; w < NTC; w++)
+              {
+                const int k = i + 2 + uy + 14 * u, j = i + 2 + ux + 16 * w;
+                c[u][w] = (k < h && j < h && j >= k) ? a[k * S + j] : 0.0;
+              }
+#pragma unroll
+          for (int u = 0; u < NTR; u++)
+#pragma unroll
+            for (int w = 0; w < NTC; w++)
+              c[u][w] = __dsub_rn (c[u][w], __dmul_rn (__dmul_rn (rk[u], rj[w]), di));
+#pragma unroll
+          for (int u = 0; u < NTR; u++)
+#pragma unroll
+            for (int w = 0; w < NTC; w++)
+              {
+                const int k = i + 2 + uy + 14 * u, j = i + 2 + ux + 16 * w;
+                if (k < h && j < h && j >= k)
+                  a[k * S + j] = c[u][w];
+              }
         }
-#pragma unroll
-      for (int u = 0; u < NT; u++)
-#pragma unroll
-        for (int w = 0; w < NT; w++)
-          {
-            const int k = i + 1 + ty + 16 * u, j = i + 1 + tx + 16 * w;
-            c[u][w] = (k < h && j < h && j >= k) ? a[k * S + j] : 0.0;
-          }
-#pragma unroll
-      for (int u = 0; u < NT; u++)
-#pragma unroll
-        for (int w = 0; w < NT; w++)
-          c[u][w] = __dsub_rn (c[u][w], __dmul_rn (__dmul_rn (rk[u], rj[w]), di));
-#pragma unroll
-      for (int u = 0; u < NT; u++)
-#pragma unroll
-        for (int w = 0; w < NT; w++)
-          {
-            const int k = i + 1 + ty + 16 * u, j = i + 1 + tx + 16 * w;
-            if (k < h && j < h && j >= k)
-              a[k * S + j] = c[u][w];
-          }
       __syncthreads ();
     }
 #ifdef MS_DIAG_TIMING
@@ -189,25 +242,30 @@ diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *
 }
 
 // d_out: h doubles (device), wt_out: chunk-major [MS_SUB/16][MS_SUB][16] or null.  The inverse is
-// computed only when someone consumes it (wt_out / inv_out).
+// computed only when someone consumes it (wt_out / inv_out).  pre_diag/pre_ld/pre_count: diagonal to
+// run the pre-update pivot test on (the whole block row, handed to its first piece).
 int
 ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_out, double *wt_out,
-           double *inv_out, cudaStream_t s)
+           double *inv_out, const double *pre_diag, size_t pre_ld, int pre_count, cudaStream_t s)
 {
   MS_CHECK_ARG (h >= 1 && h <= 112, "diag piece must have 1..112 rows");
-  size_t smem = (2 * (size_t)h * (h + 1) + 2 * h) * sizeof (double);
+  int want_inverse = (wt_out != nullptr || inv_out != nullptr);
+  size_t smem = (((size_t)(want_inverse ? 2 : 1)) * h * (h + 1) + 2 * h) * sizeof (double);
+  if (!want_inverse)
+    smem = (2 * (size_t)h * (h + 1) + 2 * h) * sizeof (double);  // layout keeps v's slot reserved
   static bool configured = false;
   if (!configured)
     {
-      MS_CUDA (cudaFuncSetAttribute (diag_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      MS_CUDA (cudaFuncSetAttribute (diag_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      MS_CUDA (cudaFuncSetAttribute (diag_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      MS_CUDA (cudaFuncSetAttribute (diag_kernel<8, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       configured = true;
     }
-  int want_inverse = (wt_out != nullptr || inv_out != nullptr);
   if (h <= 64)
-    diag_kernel<4><<<1, 256, smem, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse, c->flags);
+    diag_kernel<5, 4><<<1, 256, smem, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse,
+                                           pre_diag, pre_ld, pre_count, c->flags);
   else
-    diag_kernel<7><<<1, 256, smem, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse, c->flags);
+    diag_kernel<8, 7><<<1, 256, smem, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse,
+                                           pre_diag, pre_ld, pre_count, c->flags);
   LAUNCH_COUNT (c);
   MS_CUDA (cudaGetLastError ());
   return MS_OK;
