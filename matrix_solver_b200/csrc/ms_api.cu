@@ -113,8 +113,8 @@ ctx_free (ms_ctx *c)
   if (c->nccl)
     ms_nccl_destroy (c);
   cudaFree (c->A);
-  cudaFree (c->PB[0]);
-  cudaFree (c->PB[1]);
+  for (int b = 0; b < MS_NPB; b++)
+    cudaFree (c->PB[b]);
   cudaFree (c->Wt);
   for (int i = 0; i < 5; i++)
     cudaFree (c->vec[i]);
@@ -136,6 +136,8 @@ ctx_free (ms_ctx *c)
     cudaStreamDestroy (c->s_main);
   if (c->s_panel)
     cudaStreamDestroy (c->s_panel);
+  if (c->s_row)
+    cudaStreamDestroy (c->s_row);
   cudaGetLastError ();
   delete c;
   return MS_OK;
@@ -199,7 +201,7 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   size_t pb_bytes = c->ld * c->hpb * sizeof (double);
   CK (cudaMalloc (&c->A, a_bytes));
   CK (cudaMemset (c->A, 0, a_bytes));
-  for (int b = 0; b < 2; b++)
+  for (int b = 0; b < MS_NPB; b++)
     {
       CK (cudaMalloc (&c->PB[b], pb_bytes));
       CK (cudaMemset (c->PB[b], 0, pb_bytes));
@@ -223,9 +225,10 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   CK (cudaDeviceGetStreamPriorityRange (&lo, &hi));
   CK (cudaStreamCreateWithPriority (&c->s_main, cudaStreamNonBlocking, lo));
   CK (cudaStreamCreateWithPriority (&c->s_panel, cudaStreamNonBlocking, hi));
+  CK (cudaStreamCreateWithPriority (&c->s_row, cudaStreamNonBlocking, hi));
   CK (cudaEventCreate (&c->ev_t0));
   CK (cudaEventCreate (&c->ev_t1));
-  c->ev_pool.resize (2 * c->nblocks + 2);
+  c->ev_pool.resize (4 * c->nblocks + 8);
   for (auto &e : c->ev_pool)
     CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
 #undef CK
@@ -291,6 +294,7 @@ ms_sync (ms_ctx *c)
   MS_CHECK_ARG (c, "null ctx");
   MS_CUDA (cudaSetDevice (c->device));
   MS_CUDA (cudaStreamSynchronize (c->s_panel));
+  MS_CUDA (cudaStreamSynchronize (c->s_row));
   MS_CUDA (cudaStreamSynchronize (c->s_main));
   return MS_OK;
 }
@@ -706,6 +710,14 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s)
   return MS_OK;
 }
 
+// Streams of the look-ahead (depth 2):
+//   s_panel (high priority): panel chain of block row I (owner) and the NCCL broadcast of panel I
+//   s_row   (high priority): "U1" — panel I applied to block row I+1 only, so that its owner can
+//                            start the next panel chain at once
+//   s_main  (low priority) : "U2a" — panel I applied to block row I+2 (what U1 of the NEXT step
+//                            waits for), then "U2b" — panel I applied to everything after it
+// Panel I+1 can therefore be factored and broadcast while the bulk updates of steps I-1 and I are
+// still running; three panel buffers rotate.
 extern "C" int
 ms_factor (ms_ctx *c, double norma, double *elapsed_s)
 {
@@ -714,8 +726,10 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
   const double thresh = 1.e-14 * norma;  // EPS * norma, src/defines.h:9
   const size_t nb = c->nblocks;
   const int P = c->nranks;
+  const bool la = c->lookahead;
   cudaStream_t sm = c->s_main;
-  cudaStream_t sp = c->lookahead ? c->s_panel : c->s_main;
+  cudaStream_t sp = la ? c->s_panel : c->s_main;
+  cudaStream_t su = la ? c->s_row : c->s_main;
   c->stats.update_flops = 0;
   c->stats.update_launches = 0;
   c->stats.update_ms = 0;
@@ -723,92 +737,97 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
   MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), sm));
   std::vector<cudaEvent_t> prof;
   MS_CUDA (cudaEventRecord (c->ev_t0, sm));
-  cudaEvent_t *ev_panel = c->ev_pool.data ();
-  cudaEvent_t *ev_strip = c->ev_pool.data () + nb + 1;
-  if (c->lookahead)
+  cudaEvent_t *ev_panel = c->ev_pool.data ();            // panel I factored (and received)
+  cudaEvent_t *ev_strip = ev_panel + nb + 2;              // block row I updated through panel I-1
+  cudaEvent_t *ev_u2a = ev_strip + nb + 2;                // block row I updated through panel I-2
+  cudaEvent_t *ev_free = ev_u2a + nb + 2;                 // main stream is done with panel I
+  if (la)
     {
       MS_CUDA (cudaEventRecord (ev_strip[0], sm));
       MS_CUDA (cudaStreamWaitEvent (sp, ev_strip[0], 0));
+      MS_CUDA (cudaStreamWaitEvent (su, ev_strip[0], 0));
     }
+  auto timed = [&] (cudaStream_t st, size_t I, int pb, size_t lr0, size_t lr1) -> int {
+    const int K = (int)c->m;  // block row I is full whenever later block rows exist
+    if (!c->profile_update)
+      return do_update (c, pb, I, lr0, lr1, K, 0, st, true);
+    cudaEvent_t a, b;
+    MS_CUDA (cudaEventCreate (&a));
+    MS_CUDA (cudaEventCreate (&b));
+    MS_CUDA (cudaEventRecord (a, st));
+    int r = do_update (c, pb, I, lr0, lr1, K, 0, st, true);
+    MS_CUDA (cudaEventRecord (b, st));
+    prof.push_back (a);
+    prof.push_back (b);
+    return r;
+  };
+  auto mine = [&] (size_t J) { return J < nb && c->owner_of_block (J) == c->rank; };
+  auto lrow_of_block = [&] (size_t J) { return (J / (size_t)P) * c->m; };
   for (size_t I = 0; I < nb; I++)
     {
-      const int pb = (int)(I & 1);
+      const int pb = (int)(I % MS_NPB);
       const int owner = c->owner_of_block (I);
-      if (c->lookahead && I > 0)
-        MS_CUDA (cudaStreamWaitEvent (sp, ev_strip[I], 0));
+      // panel buffer pb last held panel I-3: the main stream must be through with it before the
+      // panel stream overwrites it (by factoring or by receiving the broadcast)
+      if (la && I >= MS_NPB)
+        MS_CUDA (cudaStreamWaitEvent (sp, ev_free[I - MS_NPB], 0));
       if (owner == c->rank)
-        MS_TRY (factor_block_row (c, I, pb, thresh, sp));
+        {
+          if (la && I > 0)
+            MS_CUDA (cudaStreamWaitEvent (sp, ev_strip[I], 0));
+          MS_TRY (factor_block_row (c, I, pb, thresh, sp));
+        }
       if (P > 1)
         MS_TRY (ms_nccl_bcast_panel (c, I, pb, owner, sp));
-      if (I + 1 >= nb)
-        {
-          if (c->lookahead)
-            {
-              MS_CUDA (cudaEventRecord (ev_panel[I], sp));
-              MS_CUDA (cudaStreamWaitEvent (sm, ev_panel[I], 0));
-            }
-          break;
-        }
-      if (c->lookahead)
+      if (la)
         {
           MS_CUDA (cudaEventRecord (ev_panel[I], sp));
           MS_CUDA (cudaStreamWaitEvent (sm, ev_panel[I], 0));
         }
-      // local row ranges: block row I+1 (if mine) and everything after it
-      const int K = (int)c->m;  // block row I is full because block row I+1 exists
-      size_t lr_rest;           // first local row of my block rows > I+1
-      if (c->owner_of_block (I + 1) == c->rank)
+      if (I + 1 >= nb)
+        break;
+      // U1: block row I+1
+      if (mine (I + 1))
         {
-          size_t lr1 = ((I + 1) / (size_t)P) * c->m;
-          size_t lr1_end = lr1 + c->block_rows (I + 1);
-          auto run = [&] () { return do_update (c, pb, I, lr1, lr1_end, K, 0, sm, true); };
-          if (c->profile_update)
+          if (la)
             {
-              cudaEvent_t a, b;
-              MS_CUDA (cudaEventCreate (&a));
-              MS_CUDA (cudaEventCreate (&b));
-              MS_CUDA (cudaEventRecord (a, sm));
-              MS_TRY (run ());
-              MS_CUDA (cudaEventRecord (b, sm));
-              prof.push_back (a);
-              prof.push_back (b);
+              MS_CUDA (cudaStreamWaitEvent (su, ev_panel[I], 0));
+              if (I >= 1)
+                MS_CUDA (cudaStreamWaitEvent (su, ev_u2a[I + 1], 0));
             }
-          else
-            MS_TRY (run ());
-          lr_rest = lr1_end;
+          size_t lr = lrow_of_block (I + 1);
+          MS_TRY (timed (su, I, pb, lr, lr + c->block_rows (I + 1)));
+          if (la)
+            MS_CUDA (cudaEventRecord (ev_strip[I + 1], su));
+        }
+      // U2a: block row I+2 (the next U1 depends on it), then U2b: the rest
+      size_t lr_rest;
+      if (mine (I + 2))
+        {
+          size_t lr = lrow_of_block (I + 2);
+          size_t lr_end = lr + c->block_rows (I + 2);
+          MS_TRY (timed (sm, I, pb, lr, lr_end));
+          if (la)
+            MS_CUDA (cudaEventRecord (ev_u2a[I + 2], sm));
+          lr_rest = lr_end;
         }
       else
         {
-          // my first block row with global index > I+1
-          size_t Jn = I + 2;
-          while (Jn < nb && c->owner_of_block (Jn) != c->rank)
+          size_t Jn = I + 3;
+          while (Jn < nb && !mine (Jn))
             Jn++;
-          lr_rest = Jn < nb ? (Jn / (size_t)P) * c->m : c->rows_local;
+          lr_rest = Jn < nb ? lrow_of_block (Jn) : c->rows_local;
         }
-      if (c->lookahead)
-        MS_CUDA (cudaEventRecord (ev_strip[I + 1], sm));
       if (lr_rest < c->rows_local)
-        {
-          auto run = [&] () { return do_update (c, pb, I, lr_rest, c->rows_local, K, 0, sm, true); };
-          if (c->profile_update)
-            {
-              cudaEvent_t a, b;
-              MS_CUDA (cudaEventCreate (&a));
-              MS_CUDA (cudaEventCreate (&b));
-              MS_CUDA (cudaEventRecord (a, sm));
-              MS_TRY (run ());
-              MS_CUDA (cudaEventRecord (b, sm));
-              prof.push_back (a);
-              prof.push_back (b);
-            }
-          else
-            MS_TRY (run ());
-        }
+        MS_TRY (timed (sm, I, pb, lr_rest, c->rows_local));
+      if (la)
+        MS_CUDA (cudaEventRecord (ev_free[I], sm));
     }
   MS_CUDA (cudaMemcpyAsync (c->h_flags, c->flags, 8 * sizeof (int), cudaMemcpyDeviceToHost, sm));
   MS_CUDA (cudaEventRecord (c->ev_t1, sm));
   MS_CUDA (cudaEventSynchronize (c->ev_t1));
   MS_CUDA (cudaStreamSynchronize (c->s_panel));
+  MS_CUDA (cudaStreamSynchronize (c->s_row));
   float ms = 0;
   MS_CUDA (cudaEventElapsedTime (&ms, c->ev_t0, c->ev_t1));
   c->stats.factor_ms = ms;

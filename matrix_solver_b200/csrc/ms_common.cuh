@@ -55,6 +55,7 @@ constexpr int MS_BM = 64;     // tile rows of the DMMA kernel
 constexpr int MS_BN = 128;    // tile cols of the DMMA kernel
 constexpr int MS_KC = 16;     // k rows per pipeline stage
 constexpr int MS_STAGES = 4;  // TMA ring depth
+constexpr int MS_NPB = 3;     // panel buffers in rotation (look-ahead depth 2)
 constexpr int MS_TILE_CONSUMER_WARPS = 8;
 constexpr int MS_TILE_THREADS = (MS_TILE_CONSUMER_WARPS + 1) * 32;
 
@@ -90,7 +91,7 @@ struct ms_ctx
   bool panel_trsm = true;   // K3 as a triangular solve (default) or as a DMMA product with the inverse
 
   double *A = nullptr;       // rows_alloc x ld, row-major; only j >= i meaningful
-  double *PB[2] = {nullptr, nullptr};  // panel buffers, chunk-major [ld/16][hpb][16]
+  double *PB[MS_NPB] = {nullptr, nullptr, nullptr};  // panel buffers, chunk-major [ld/16][hpb][16]
   double *Wt = nullptr;      // D-scaled inverse of the current piece, chunk-major [4][64][16]
   double *vec[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // d b y x r (n each, padded)
   double *acc = nullptr;     // solve accumulators (n)
@@ -102,11 +103,11 @@ struct ms_ctx
   double *d_stage = nullptr;   // device staging for uploads/downloads
   size_t stage_doubles = 0;
 
-  cudaStream_t s_main = nullptr, s_panel = nullptr;
+  cudaStream_t s_main = nullptr, s_panel = nullptr, s_row = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 
-  CUtensorMap tm_A, tm_PB[2], tm_Wt;
+  CUtensorMap tm_A, tm_PB[MS_NPB], tm_Wt;
   bool have_tm = false;
 
   std::vector<ms_piece> pieces;

@@ -418,7 +418,7 @@ ms_tile_setup (ms_ctx *c)
   if (!c->fast)
     return MS_OK;
   MS_TRY (make_map_2d (&c->tm_A, c->A, c->ld, c->rows_alloc, c->ld * 8));
-  for (int b = 0; b < 2; b++)
+  for (int b = 0; b < MS_NPB; b++)
     MS_TRY (make_map_2d (&c->tm_PB[b], c->PB[b], MS_CHUNK, (c->ld / MS_CHUNK) * c->hpb, MS_CHUNK * 8));
   MS_TRY (make_map_2d (&c->tm_Wt, c->Wt, MS_CHUNK, (MS_SUB / MS_CHUNK) * MS_SUB, MS_CHUNK * 8));
   MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel<MS_MODE_UPDATE>,
