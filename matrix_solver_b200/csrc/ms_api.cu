@@ -229,8 +229,9 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   CK (cudaEventCreate (&c->ev_t0));
   CK (cudaEventCreate (&c->ev_t1));
   c->ev_pool.resize (4 * c->nblocks + 8);
+  c->trace = getenv ("MS_TRACE") && atoi (getenv ("MS_TRACE"));
   for (auto &e : c->ev_pool)
-    CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+    CK (cudaEventCreateWithFlags (&e, c->trace ? cudaEventDefault : cudaEventDisableTiming));
 #undef CK
   int r = ms_tile_setup (c);
   if (r < 0)
@@ -841,10 +842,40 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
     }
   for (auto e : prof)
     cudaEventDestroy (e);
+  if (c->trace && la)
+    {
+      c->trace_panel.assign (nb, -1.f);
+      c->trace_free.assign (nb, -1.f);
+      c->trace_strip.assign (nb, -1.f);
+      for (size_t I = 0; I < nb; I++)
+        {
+          cudaEventElapsedTime (&c->trace_panel[I], c->ev_t0, ev_panel[I]);
+          if (I + 1 < nb)
+            cudaEventElapsedTime (&c->trace_free[I], c->ev_t0, ev_free[I]);
+          if (I > 0 && mine (I))
+            cudaEventElapsedTime (&c->trace_strip[I], c->ev_t0, ev_strip[I]);
+        }
+      cudaGetLastError ();
+    }
   int failed = c->h_flags[0] != 0;
   if (P > 1)
     MS_TRY (ms_nccl_agree_flag (c, &failed));
   return failed ? MS_NUMERICAL_FAILURE : MS_OK;
+}
+
+// debug hook (not in the public header): per-step timeline of the last ms_factor in ms since its
+// start — panel I available, main stream done with panel I, block row I ready to factor (owner)
+extern "C" int
+ms_debug_trace (ms_ctx *c, float *panel_ms, float *free_ms, float *strip_ms, size_t cap)
+{
+  MS_CHECK_ARG (c && c->trace, "create the context with MS_TRACE=1");
+  for (size_t i = 0; i < c->trace_panel.size () && i < cap; i++)
+    {
+      panel_ms[i] = c->trace_panel[i];
+      free_ms[i] = c->trace_free[i];
+      strip_ms[i] = c->trace_strip[i];
+    }
+  return (int)c->trace_panel.size ();
 }
 
 // ----------------------------------------------------------------------------- solves

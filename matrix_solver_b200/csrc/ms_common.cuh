@@ -88,6 +88,8 @@ struct ms_ctx
   bool force_generic = false;
   bool lookahead = true;
   bool profile_update = false;
+  bool trace = false;       // MS_TRACE=1: timing-enabled step events, read back by ms_debug_trace
+  std::vector<float> trace_panel, trace_free, trace_strip;
   bool panel_trsm = true;   // K3 as a triangular solve (default) or as a DMMA product with the inverse
 
   double *A = nullptr;       // rows_alloc x ld, row-major; only j >= i meaningful

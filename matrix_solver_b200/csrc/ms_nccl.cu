@@ -20,6 +20,7 @@ struct nccl_api
   void *lib = nullptr;
   ncclResult_t (*GetUniqueId) (ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank) (ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitRankConfig) (ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *) = nullptr;
   ncclResult_t (*CommDestroy) (ncclComm_t) = nullptr;
   ncclResult_t (*Broadcast) (const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Reduce) (const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -64,6 +65,7 @@ load_nccl ()
   SYM (GroupEnd, "ncclGroupEnd");
   SYM (GetErrorString, "ncclGetErrorString");
 #undef SYM
+  *(void **)(&g_nccl.CommInitRankConfig) = dlsym (h, "ncclCommInitRankConfig");  // optional
   g_nccl.lib = h;
   return MS_OK;
 }
@@ -102,7 +104,21 @@ ms_nccl_init (ms_ctx *c, const void *id128)
   ncclUniqueId id;
   memcpy (&id, id128, sizeof (id));
   ncclComm_t comm;
-  MS_NCCL (g_nccl.CommInitRank (&comm, c->nranks, id, c->rank));
+  // The receivers' broadcast kernels are posted early (look-ahead) and then spin until the owner
+  // sends; every CTA they hold is an SM slot the trailing update cannot use.  The panel needs only a
+  // few tens of GB/s (134 MB per ~4 ms step at n = 65536 on 8 GPUs), so cap the communicator's CTAs.
+  int max_ctas = 0;  // 0 = NCCL default; see profiles/README.md for the sweep
+  if (const char *e = getenv ("MS_NCCL_CTAS"))
+    max_ctas = atoi (e);
+  if (g_nccl.CommInitRankConfig && max_ctas > 0)
+    {
+      ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+      cfg.minCTAs = 1;
+      cfg.maxCTAs = max_ctas;
+      MS_NCCL (g_nccl.CommInitRankConfig (&comm, c->nranks, id, c->rank, &cfg));
+    }
+  else
+    MS_NCCL (g_nccl.CommInitRank (&comm, c->nranks, id, c->rank));
   c->nccl = (void *)comm;
   return MS_OK;
 }
