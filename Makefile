@@ -11,9 +11,9 @@ HOST := matrix_solver_b200/host
 LIBDIR := matrix_solver_b200/lib
 BINDIR := matrix_solver_b200/bin
 CU := $(CSRC)/ms_api.cu $(CSRC)/ms_kernels_util.cu $(CSRC)/ms_kernels_diag.cu \
-      $(CSRC)/ms_kernels_tile.cu $(CSRC)/ms_kernels_solve.cu $(CSRC)/ms_nccl.cu
+      $(CSRC)/ms_kernels_tile.cu $(CSRC)/ms_kernels_solve.cu $(CSRC)/ms_nccl.cu $(CSRC)/ms_p2p.cu
 OBJ := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU))
-HDR := $(CSRC)/ms_common.cuh $(CSRC)/ms_nccl.h include/ms_b200.h
+HDR := $(CSRC)/ms_common.cuh $(CSRC)/ms_nccl.h $(CSRC)/ms_p2p.h include/ms_b200.h
 
 .PHONY: all lib cli oracle clean
 all: lib cli oracle

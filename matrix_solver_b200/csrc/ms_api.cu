@@ -17,6 +17,7 @@
 
 #include "ms_common.cuh"
 #include "ms_nccl.h"
+#include "ms_p2p.h"
 
 static thread_local char g_err[1024] = "";
 
@@ -110,6 +111,8 @@ ctx_free (ms_ctx *c)
     return MS_OK;
   cudaSetDevice (c->device);
   cudaDeviceSynchronize ();
+  if (c->p2p)
+    ms_p2p_destroy (c);
   if (c->nccl)
     ms_nccl_destroy (c);
   cudaFree (c->A);
@@ -239,6 +242,9 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   if (nranks > 1)
     {
       r = ms_nccl_init (c, unique_id);
+      if (r < 0)
+        return fail (r);
+      r = ms_p2p_init (c);
       if (r < 0)
         return fail (r);
     }
@@ -728,6 +734,8 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
   const size_t nb = c->nblocks;
   const int P = c->nranks;
   const bool la = c->lookahead;
+  const bool p2p = ms_p2p_enabled (c);
+  ms_p2p_begin_factor (c);
   cudaStream_t sm = c->s_main;
   cudaStream_t sp = la ? c->s_panel : c->s_main;
   cudaStream_t su = la ? c->s_row : c->s_main;
@@ -778,13 +786,16 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
             MS_CUDA (cudaStreamWaitEvent (sp, ev_strip[I], 0));
           MS_TRY (factor_block_row (c, I, pb, thresh, sp));
         }
-      if (P > 1)
+      if (P > 1 && !p2p)
         MS_TRY (ms_nccl_bcast_panel (c, I, pb, owner, sp));
+      if (P > 1 && p2p && owner != c->rank)
+        MS_TRY (ms_p2p_wait_panel (c, I, pb, owner, sp));
+      if (la || p2p)
+        MS_CUDA (cudaEventRecord (ev_panel[I], sp));
       if (la)
-        {
-          MS_CUDA (cudaEventRecord (ev_panel[I], sp));
-          MS_CUDA (cudaStreamWaitEvent (sm, ev_panel[I], 0));
-        }
+        MS_CUDA (cudaStreamWaitEvent (sm, ev_panel[I], 0));
+      if (P > 1 && p2p && owner == c->rank)
+        MS_TRY (ms_p2p_send_panel (c, I, pb, ev_panel[I]));
       if (I + 1 >= nb)
         break;
       // U1: block row I+1
@@ -821,8 +832,10 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
         }
       if (lr_rest < c->rows_local)
         MS_TRY (timed (sm, I, pb, lr_rest, c->rows_local));
-      if (la)
+      if (la || p2p)
         MS_CUDA (cudaEventRecord (ev_free[I], sm));
+      if (p2p)
+        MS_TRY (ms_p2p_release_panel (c, I, ev_free[I]));
     }
   MS_CUDA (cudaMemcpyAsync (c->h_flags, c->flags, 8 * sizeof (int), cudaMemcpyDeviceToHost, sm));
   MS_CUDA (cudaEventRecord (c->ev_t1, sm));

@@ -116,6 +116,7 @@ struct ms_ctx
   std::vector<size_t> block_first_piece;  // index into pieces, size nblocks+1
 
   void *nccl = nullptr;  // ncclComm_t when nranks > 1
+  void *p2p = nullptr;   // copy-engine panel transport (ms_p2p.cu) when nranks > 1
 
   ms_stats stats = {};
   int sm_count = 148;

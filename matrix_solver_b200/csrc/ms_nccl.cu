@@ -25,6 +25,7 @@ struct nccl_api
   ncclResult_t (*Broadcast) (const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Reduce) (const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce) (const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather) (const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart) () = nullptr;
   ncclResult_t (*GroupEnd) () = nullptr;
   const char *(*GetErrorString) (ncclResult_t) = nullptr;
@@ -61,6 +62,7 @@ load_nccl ()
   SYM (Broadcast, "ncclBroadcast");
   SYM (Reduce, "ncclReduce");
   SYM (AllReduce, "ncclAllReduce");
+  SYM (AllGather, "ncclAllGather");
   SYM (GroupStart, "ncclGroupStart");
   SYM (GroupEnd, "ncclGroupEnd");
   SYM (GetErrorString, "ncclGetErrorString");
@@ -170,6 +172,13 @@ int
 ms_nccl_allreduce_sum (ms_ctx *c, double *p, size_t cnt, cudaStream_t s)
 {
   MS_NCCL (g_nccl.AllReduce (p, p, cnt, ncclDouble, ncclSum, (ncclComm_t)c->nccl, s));
+  return MS_OK;
+}
+
+int
+ms_nccl_allgather_bytes (ms_ctx *c, const void *send, void *recv, size_t bytes_per_rank, cudaStream_t s)
+{
+  MS_NCCL (g_nccl.AllGather (send, recv, bytes_per_rank, ncclChar, (ncclComm_t)c->nccl, s));
   return MS_OK;
 }
 

@@ -12,5 +12,6 @@ int ms_nccl_bcast_panel (ms_ctx *c, size_t I, int pb, int owner, cudaStream_t s)
 int ms_nccl_bcast (ms_ctx *c, double *p, size_t cnt, int root, cudaStream_t s);
 int ms_nccl_reduce_sum (ms_ctx *c, double *p, size_t cnt, int root, cudaStream_t s);
 int ms_nccl_allreduce_sum (ms_ctx *c, double *p, size_t cnt, cudaStream_t s);
+int ms_nccl_allgather_bytes (ms_ctx *c, const void *send, void *recv, size_t bytes_per_rank, cudaStream_t s);
 // OR of a host flag over all ranks (check_res, src/init.cpp:565-581)
 int ms_nccl_agree_flag (ms_ctx *c, int *flag);

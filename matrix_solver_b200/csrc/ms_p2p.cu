@@ -1,0 +1,230 @@
+// ms_p2p.cu — see ms_p2p.h.
+#include <nccl.h>
+
+#include "ms_nccl.h"
+#include "ms_p2p.h"
+
+namespace
+{
+constexpr int SIG_INTS = 256;      // [0..2] ready per panel buffer, [16 + r] credit from rank r
+constexpr int SIG_READY = 0;
+constexpr int SIG_CREDIT = 16;
+constexpr int STAGE_SLOTS = 64;
+
+struct p2p_state
+{
+  bool on = false;
+  int *sig = nullptr;                       // this rank's flags (peers write, we wait)
+  int *stage = nullptr;                     // local source words for the 4-byte signal copies
+  int stage_next = 0;
+  std::vector<double *> peer_pb[MS_NPB];    // peers' panel buffers (IPC mapped), [rank]
+  std::vector<double *> peer_d;             // peers' d vectors
+  std::vector<int *> peer_sig;
+  std::vector<void *> opened;
+  cudaStream_t s_copy = nullptr;
+  cudaEvent_t ev_tmp = nullptr;
+  unsigned epoch = 0;                       // grows by (nblocks + 8) per factorisation
+  CUresult (*waitValue32) (CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+  CUresult (*writeValue32) (CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+};
+
+p2p_state *
+st (const ms_ctx *c)
+{
+  return (p2p_state *)c->p2p;
+}
+
+int
+driver_fn (const char *name, void **fn)
+{
+  cudaDriverEntryPointQueryResult q;
+  MS_CUDA (cudaGetDriverEntryPoint (name, fn, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !*fn)
+    {
+      ms_set_error ("driver entry point %s unavailable", name);
+      return MS_ERR_CUDA;
+    }
+  return MS_OK;
+}
+
+// post `value` into the int at `remote` (a peer or local device address), ordered on stream s
+int
+post_value (p2p_state *p, int *remote, unsigned value, cudaStream_t s)
+{
+  int *slot = p->stage + (p->stage_next++ % STAGE_SLOTS);
+  CUresult r = p->writeValue32 ((CUstream)s, (CUdeviceptr)slot, value, 0);
+  if (r != CUDA_SUCCESS)
+    {
+      ms_set_error ("cuStreamWriteValue32 failed: %d", (int)r);
+      return MS_ERR_CUDA;
+    }
+  MS_CUDA (cudaMemcpyAsync (remote, slot, sizeof (int), cudaMemcpyDefault, s));
+  return MS_OK;
+}
+
+int
+wait_value (p2p_state *p, int *addr, unsigned value, cudaStream_t s)
+{
+  CUresult r = p->waitValue32 ((CUstream)s, (CUdeviceptr)addr, value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS)
+    {
+      ms_set_error ("cuStreamWaitValue32 failed: %d", (int)r);
+      return MS_ERR_CUDA;
+    }
+  return MS_OK;
+}
+}  // namespace
+
+bool
+ms_p2p_enabled (const ms_ctx *c)
+{
+  return c->p2p && st (c)->on;
+}
+
+int
+ms_p2p_init (ms_ctx *c)
+{
+  const char *e = getenv ("MS_P2P");
+  if (e && !atoi (e))
+    return MS_OK;  // NCCL broadcast instead
+  p2p_state *p = new p2p_state ();
+  c->p2p = p;
+  const int P = c->nranks;
+  MS_TRY (driver_fn ("cuStreamWaitValue32", (void **)&p->waitValue32));
+  MS_TRY (driver_fn ("cuStreamWriteValue32", (void **)&p->writeValue32));
+  MS_CUDA (cudaMalloc (&p->sig, SIG_INTS * sizeof (int)));
+  MS_CUDA (cudaMemset (p->sig, 0, SIG_INTS * sizeof (int)));
+  MS_CUDA (cudaMalloc (&p->stage, STAGE_SLOTS * sizeof (int)));
+  MS_CUDA (cudaStreamCreateWithFlags (&p->s_copy, cudaStreamNonBlocking));
+  MS_CUDA (cudaEventCreateWithFlags (&p->ev_tmp, cudaEventDisableTiming));
+
+  // exchange IPC handles: [PB0 PB1 PB2 d sig] per rank, gathered with the NCCL communicator
+  constexpr int NH = MS_NPB + 2;
+  const size_t hb = sizeof (cudaIpcMemHandle_t);
+  std::vector<char> mine (NH * hb), all ((size_t)P * NH * hb);
+  void *ptrs[NH];
+  for (int b = 0; b < MS_NPB; b++)
+    ptrs[b] = c->PB[b];
+  ptrs[MS_NPB] = c->vec[MS_VEC_D];
+  ptrs[MS_NPB + 1] = p->sig;
+  for (int i = 0; i < NH; i++)
+    MS_CUDA (cudaIpcGetMemHandle ((cudaIpcMemHandle_t *)(mine.data () + i * hb), ptrs[i]));
+  char *dbuf = nullptr;
+  MS_CUDA (cudaMalloc (&dbuf, all.size ()));
+  MS_CUDA (cudaMemcpy (dbuf + (size_t)c->rank * NH * hb, mine.data (), mine.size (), cudaMemcpyHostToDevice));
+  MS_TRY (ms_nccl_allgather_bytes (c, dbuf + (size_t)c->rank * NH * hb, dbuf, NH * hb, c->s_main));
+  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  MS_CUDA (cudaMemcpy (all.data (), dbuf, all.size (), cudaMemcpyDeviceToHost));
+  MS_CUDA (cudaFree (dbuf));
+
+  for (int b = 0; b < MS_NPB; b++)
+    p->peer_pb[b].assign (P, nullptr);
+  p->peer_d.assign (P, nullptr);
+  p->peer_sig.assign (P, nullptr);
+  for (int r = 0; r < P; r++)
+    {
+      if (r == c->rank)
+        continue;
+      for (int i = 0; i < NH; i++)
+        {
+          void *q = nullptr;
+          cudaError_t err = cudaIpcOpenMemHandle (&q, *(cudaIpcMemHandle_t *)(all.data () + ((size_t)r * NH + i) * hb),
+                                                  cudaIpcMemLazyEnablePeerAccess);
+          if (err != cudaSuccess)
+            {
+              ms_set_error ("cudaIpcOpenMemHandle (rank %d, buffer %d) -> %s", r, i, cudaGetErrorString (err));
+              return MS_ERR_CUDA;
+            }
+          p->opened.push_back (q);
+          if (i < MS_NPB)
+            p->peer_pb[i][r] = (double *)q;
+          else if (i == MS_NPB)
+            p->peer_d[r] = (double *)q;
+          else
+            p->peer_sig[r] = (int *)q;
+        }
+    }
+  // nobody may start posting into a peer before that peer has finished this setup
+  MS_TRY (ms_nccl_allreduce_sum (c, c->acc, 1, c->s_main));
+  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  p->on = true;
+  return MS_OK;
+}
+
+void
+ms_p2p_destroy (ms_ctx *c)
+{
+  p2p_state *p = st (c);
+  if (!p)
+    return;
+  cudaDeviceSynchronize ();
+  for (void *q : p->opened)
+    cudaIpcCloseMemHandle (q);
+  cudaFree (p->sig);
+  cudaFree (p->stage);
+  if (p->s_copy)
+    cudaStreamDestroy (p->s_copy);
+  if (p->ev_tmp)
+    cudaEventDestroy (p->ev_tmp);
+  delete p;
+  c->p2p = nullptr;
+}
+
+void
+ms_p2p_begin_factor (ms_ctx *c)
+{
+  if (ms_p2p_enabled (c))
+    st (c)->epoch += (unsigned)c->nblocks + 8;
+}
+
+int
+ms_p2p_send_panel (ms_ctx *c, size_t I, int pb, cudaEvent_t factored)
+{
+  p2p_state *p = st (c);
+  const int P = c->nranks;
+  cudaStream_t s = p->s_copy;
+  MS_CUDA (cudaStreamWaitEvent (s, factored, 0));
+  const bool has_trailing = (I + 1) * c->m < c->n;
+  const size_t chunk0 = (I * c->m) / MS_CHUNK;
+  const size_t off = chunk0 * c->hpb * MS_CHUNK;
+  const size_t cnt = (c->ld / MS_CHUNK - chunk0) * c->hpb * MS_CHUNK;
+  const size_t rows = c->block_rows (I);
+  // the next owner sits on the critical path (it factors block row I+1): serve it first
+  for (int k = 1; k < P; k++)
+    {
+      const int r = (int)((I + (size_t)k) % (size_t)P) == c->rank ? -1 : (int)((I + (size_t)k) % (size_t)P);
+      if (r < 0)
+        continue;
+      // credit: this peer must be done with the panel that used its buffer before (panel I - 3)
+      if (I >= MS_NPB)
+        MS_TRY (wait_value (p, p->sig + SIG_CREDIT + r, p->epoch + (unsigned)(I - MS_NPB) + 1, s));
+      if (has_trailing)
+        MS_CUDA (cudaMemcpyAsync (p->peer_pb[pb][r] + off, c->PB[pb] + off, cnt * sizeof (double), cudaMemcpyDefault, s));
+      MS_CUDA (cudaMemcpyAsync (p->peer_d[r] + I * c->m, c->vec[MS_VEC_D] + I * c->m, rows * sizeof (double),
+                                cudaMemcpyDefault, s));
+      MS_TRY (post_value (p, p->peer_sig[r] + SIG_READY + pb, p->epoch + (unsigned)I + 1, s));
+    }
+  return MS_OK;
+}
+
+int
+ms_p2p_wait_panel (ms_ctx *c, size_t I, int pb, int owner, cudaStream_t s)
+{
+  (void)owner;
+  p2p_state *p = st (c);
+  return wait_value (p, p->sig + SIG_READY + pb, p->epoch + (unsigned)I + 1, s);
+}
+
+int
+ms_p2p_release_panel (ms_ctx *c, size_t I, cudaEvent_t freed)
+{
+  p2p_state *p = st (c);
+  const size_t J = I + MS_NPB;  // the panel that will overwrite this buffer
+  if (J >= c->nblocks)
+    return MS_OK;
+  const int next_owner = c->owner_of_block (J);
+  if (next_owner == c->rank)
+    return MS_OK;  // own buffer: ordered by the ev_free wait of the panel stream
+  MS_CUDA (cudaStreamWaitEvent (p->s_copy, freed, 0));
+  return post_value (p, p->peer_sig[next_owner] + SIG_CREDIT + c->rank, p->epoch + (unsigned)I + 1, p->s_copy);
+}
