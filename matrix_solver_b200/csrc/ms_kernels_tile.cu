@@ -438,7 +438,11 @@ tile_total (const tile_args &ta, int mode)
   return (int)std::min<long long> (total, 0x7fffffff);
 }
 
-// At least ~8 waves of CTAs (2 per SM) so that the tail stays small; at most MS_TILES_PER_CTA.
+// Tiles per CTA.  Running CTAs are never preempted: the high-priority panel chain (diag, TRSM, the
+// next block row's update) only gets an SM slot when a low-priority tile CTA retires, so the CTA
+// lifetime is the chain's ramp-up latency.  With several GPUs the chain paces everybody
+// (profiles/README.md: 2 ms per chain with 4 tiles per CTA vs 0.3 ms on an idle GPU), so CTAs
+// walk a single tile there; on one GPU up to 4 tiles per CTA amortise the prologue (+1 %).
 static int g_tiles_per_cta_max = -1;
 static int
 tiles_per_cta_for (const ms_ctx *c, int total)
@@ -446,10 +450,11 @@ tiles_per_cta_for (const ms_ctx *c, int total)
   if (g_tiles_per_cta_max < 0)
     {
       const char *e = getenv ("MS_TILES_PER_CTA");
-      g_tiles_per_cta_max = e ? std::max (1, atoi (e)) : 4;
+      g_tiles_per_cta_max = e ? std::max (1, atoi (e)) : 0;
     }
+  int cap = g_tiles_per_cta_max > 0 ? g_tiles_per_cta_max : (c->nranks > 1 ? 1 : 4);
   int t = total / (2 * c->sm_count * 8);
-  return std::max (1, std::min (t, g_tiles_per_cta_max));
+  return std::max (1, std::min (t, cap));
 }
 
 // Update local rows [lrow_begin, lrow_end) (64-row tiles of block rows J > I, or the later pieces

@@ -15,13 +15,15 @@ struct p2p_state
 {
   bool on = false;
   int *sig = nullptr;                       // this rank's flags (peers write, we wait)
-  int *stage = nullptr;                     // local source words for the 4-byte signal copies
-  int stage_next = 0;
+  int *stage = nullptr;                     // local source words for the 4-byte signal copies:
+  std::vector<int> stage_next;              // one ring of STAGE_SLOTS per stream (index = peer, P = misc)
   std::vector<double *> peer_pb[MS_NPB];    // peers' panel buffers (IPC mapped), [rank]
   std::vector<double *> peer_d;             // peers' d vectors
   std::vector<int *> peer_sig;
   std::vector<void *> opened;
-  cudaStream_t s_copy = nullptr;
+  std::vector<cudaStream_t> s_peer;         // one copy stream per peer: transfers to different
+                                            // peers run on different copy engines / links
+  cudaStream_t s_misc = nullptr;            // credits
   cudaEvent_t ev_tmp = nullptr;
   unsigned epoch = 0;                       // grows by (nblocks + 8) per factorisation
   CUresult (*waitValue32) (CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
@@ -47,11 +49,12 @@ driver_fn (const char *name, void **fn)
   return MS_OK;
 }
 
-// post `value` into the int at `remote` (a peer or local device address), ordered on stream s
+// post `value` into the int at `remote` (a peer or local device address), ordered on stream s;
+// `ring` selects the staging ring that belongs to that stream
 int
-post_value (p2p_state *p, int *remote, unsigned value, cudaStream_t s)
+post_value (p2p_state *p, int ring, int *remote, unsigned value, cudaStream_t s)
 {
-  int *slot = p->stage + (p->stage_next++ % STAGE_SLOTS);
+  int *slot = p->stage + (size_t)ring * STAGE_SLOTS + (p->stage_next[ring]++ % STAGE_SLOTS);
   CUresult r = p->writeValue32 ((CUstream)s, (CUdeviceptr)slot, value, 0);
   if (r != CUDA_SUCCESS)
     {
@@ -94,8 +97,13 @@ ms_p2p_init (ms_ctx *c)
   MS_TRY (driver_fn ("cuStreamWriteValue32", (void **)&p->writeValue32));
   MS_CUDA (cudaMalloc (&p->sig, SIG_INTS * sizeof (int)));
   MS_CUDA (cudaMemset (p->sig, 0, SIG_INTS * sizeof (int)));
-  MS_CUDA (cudaMalloc (&p->stage, STAGE_SLOTS * sizeof (int)));
-  MS_CUDA (cudaStreamCreateWithFlags (&p->s_copy, cudaStreamNonBlocking));
+  MS_CUDA (cudaMalloc (&p->stage, (size_t)(P + 1) * STAGE_SLOTS * sizeof (int)));
+  p->stage_next.assign (P + 1, 0);
+  p->s_peer.assign (P, nullptr);
+  for (int r = 0; r < P; r++)
+    if (r != c->rank)
+      MS_CUDA (cudaStreamCreateWithFlags (&p->s_peer[r], cudaStreamNonBlocking));
+  MS_CUDA (cudaStreamCreateWithFlags (&p->s_misc, cudaStreamNonBlocking));
   MS_CUDA (cudaEventCreateWithFlags (&p->ev_tmp, cudaEventDisableTiming));
 
   // exchange IPC handles: [PB0 PB1 PB2 d sig] per rank, gathered with the NCCL communicator
@@ -162,8 +170,11 @@ ms_p2p_destroy (ms_ctx *c)
     cudaIpcCloseMemHandle (q);
   cudaFree (p->sig);
   cudaFree (p->stage);
-  if (p->s_copy)
-    cudaStreamDestroy (p->s_copy);
+  for (cudaStream_t t : p->s_peer)
+    if (t)
+      cudaStreamDestroy (t);
+  if (p->s_misc)
+    cudaStreamDestroy (p->s_misc);
   if (p->ev_tmp)
     cudaEventDestroy (p->ev_tmp);
   delete p;
@@ -182,8 +193,6 @@ ms_p2p_send_panel (ms_ctx *c, size_t I, int pb, cudaEvent_t factored)
 {
   p2p_state *p = st (c);
   const int P = c->nranks;
-  cudaStream_t s = p->s_copy;
-  MS_CUDA (cudaStreamWaitEvent (s, factored, 0));
   const bool has_trailing = (I + 1) * c->m < c->n;
   const size_t chunk0 = (I * c->m) / MS_CHUNK;
   const size_t off = chunk0 * c->hpb * MS_CHUNK;
@@ -195,6 +204,8 @@ ms_p2p_send_panel (ms_ctx *c, size_t I, int pb, cudaEvent_t factored)
       const int r = (int)((I + (size_t)k) % (size_t)P) == c->rank ? -1 : (int)((I + (size_t)k) % (size_t)P);
       if (r < 0)
         continue;
+      cudaStream_t s = p->s_peer[r];
+      MS_CUDA (cudaStreamWaitEvent (s, factored, 0));
       // credit: this peer must be done with the panel that used its buffer before (panel I - 3)
       if (I >= MS_NPB)
         MS_TRY (wait_value (p, p->sig + SIG_CREDIT + r, p->epoch + (unsigned)(I - MS_NPB) + 1, s));
@@ -202,7 +213,7 @@ ms_p2p_send_panel (ms_ctx *c, size_t I, int pb, cudaEvent_t factored)
         MS_CUDA (cudaMemcpyAsync (p->peer_pb[pb][r] + off, c->PB[pb] + off, cnt * sizeof (double), cudaMemcpyDefault, s));
       MS_CUDA (cudaMemcpyAsync (p->peer_d[r] + I * c->m, c->vec[MS_VEC_D] + I * c->m, rows * sizeof (double),
                                 cudaMemcpyDefault, s));
-      MS_TRY (post_value (p, p->peer_sig[r] + SIG_READY + pb, p->epoch + (unsigned)I + 1, s));
+      MS_TRY (post_value (p, r, p->peer_sig[r] + SIG_READY + pb, p->epoch + (unsigned)I + 1, s));
     }
   return MS_OK;
 }
@@ -225,6 +236,7 @@ ms_p2p_release_panel (ms_ctx *c, size_t I, cudaEvent_t freed)
   const int next_owner = c->owner_of_block (J);
   if (next_owner == c->rank)
     return MS_OK;  // own buffer: ordered by the ev_free wait of the panel stream
-  MS_CUDA (cudaStreamWaitEvent (p->s_copy, freed, 0));
-  return post_value (p, p->peer_sig[next_owner] + SIG_CREDIT + c->rank, p->epoch + (unsigned)I + 1, p->s_copy);
+  MS_CUDA (cudaStreamWaitEvent (p->s_misc, freed, 0));
+  return post_value (p, c->nranks, p->peer_sig[next_owner] + SIG_CREDIT + c->rank, p->epoch + (unsigned)I + 1,
+                     p->s_misc);
 }
