@@ -30,15 +30,18 @@ warp_tri_solve (const double *Rs, double *rhs_sol, int h, double thresh, int *fl
   const int lane = threadIdx.x & 31;
   double t0 = lane < h ? rhs_sol[lane] : 0.0;
   double t1 = lane + 32 < h ? rhs_sol[lane + 32] : 0.0;
+  // reciprocals of the pivots up front (two divisions per lane, in parallel) so that the 64
+  // dependent steps below are shuffle + multiply + FMA instead of shuffle + IEEE divide
+  const double p0 = lane < h ? Rs[lane * 65 + lane] : 1.0;
+  const double p1 = lane + 32 < h ? Rs[(lane + 32) * 65 + lane + 32] : 1.0;
+  if ((lane < h && fabs (p0) < thresh) || (lane + 32 < h && fabs (p1) < thresh))
+    flags[0] = 1;
+  const double r0 = 1.0 / p0, r1 = 1.0 / p1;
   if (FORWARD)
     {
       for (int i = 0; i < h; i++)
         {
-          double piv = Rs[i * 65 + i];
-          double ti = __shfl_sync (0xffffffffu, i < 32 ? t0 : t1, i & 31);
-          double yi = ti / piv;
-          if (lane == 0 && fabs (piv) < thresh)
-            flags[0] = 1;
+          const double yi = __shfl_sync (0xffffffffu, i < 32 ? t0 * r0 : t1 * r1, i & 31);
           if (lane == (i & 31))
             {
               if (i < 32)
@@ -57,11 +60,7 @@ warp_tri_solve (const double *Rs, double *rhs_sol, int h, double thresh, int *fl
     {
       for (int i = h - 1; i >= 0; i--)
         {
-          double piv = Rs[i * 65 + i];
-          double ti = __shfl_sync (0xffffffffu, i < 32 ? t0 : t1, i & 31);
-          double xi = ti / piv;
-          if (lane == 0 && fabs (piv) < thresh)
-            flags[0] = 1;
+          const double xi = __shfl_sync (0xffffffffu, i < 32 ? t0 * r0 : t1 * r1, i & 31);
           if (lane == (i & 31))
             {
               if (i < 32)
@@ -94,25 +93,36 @@ forward_step_kernel (const double *__restrict__ A, size_t ld, size_t lrow0, size
       int i = e / h, j = e - i * h;
       Rs[i * 65 + j] = j >= i ? A[(lrow0 + i) * ld + r0 + j] : 0.0;
     }
-  if (threadIdx.x < h)
-    ys[threadIdx.x] = b[r0 + threadIdx.x] - acc[r0 + threadIdx.x];
+  if (threadIdx.x < 64)
+    ys[threadIdx.x] = threadIdx.x < h ? b[r0 + threadIdx.x] - acc[r0 + threadIdx.x] : 0.0;
   __syncthreads ();
   if (threadIdx.x < 32)
     warp_tri_solve<true> (Rs, ys, h, thresh, blockIdx.x == 0 ? flags : flags + 1);
   __syncthreads ();
   if (blockIdx.x == 0 && threadIdx.x < h)
     y[r0 + threadIdx.x] = ys[threadIdx.x];
-  // trailing columns: acc_j += sum_i R(i, j) y_i
-  size_t j = r0 + h + (size_t)blockIdx.x * SOLVE_THREADS + threadIdx.x;
+  // trailing columns: acc_j += sum_i R(i, j) y_i.  The CTA owns 64 columns; its four 64-thread
+  // groups take 16 rows of the piece each, so every thread has its 16 loads in flight at once
+  // (the walk is HBM-latency bound otherwise) and a row segment is a 512-byte coalesced read.
+  __shared__ double part[4][64];
+  const int cx = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const size_t j = r0 + h + (size_t)blockIdx.x * 64 + cx;
+  double s = 0.0;
   if (j < n)
     {
-      const double *col = A + lrow0 * ld + j;
-      double s = 0.0;
-#pragma unroll 8
-      for (int i = 0; i < h; i++)
-        s += col[(size_t)i * ld] * ys[i];
-      acc[j] += s;
+      const double *col = A + (lrow0 + (size_t)rg * 16) * ld + j;
+      double v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        v[i] = (rg * 16 + i < h) ? col[(size_t)i * ld] : 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        s += v[i] * ys[rg * 16 + i];
     }
+  part[rg][cx] = s;
+  __syncthreads ();
+  if (rg == 0 && j < n)
+    acc[j] += (part[0][cx] + part[1][cx]) + (part[2][cx] + part[3][cx]);
 }
 
 __global__ void __launch_bounds__ (SOLVE_THREADS)
@@ -171,7 +181,7 @@ int
 ms_k_forward_step (ms_ctx *c, const ms_piece &pc, double thresh, cudaStream_t s)
 {
   size_t rest = c->n - (pc.row0 + (size_t)pc.h);
-  unsigned grid = (unsigned)((rest + SOLVE_THREADS - 1) / SOLVE_THREADS);
+  unsigned grid = (unsigned)((rest + 63) / 64);
   if (grid == 0)
     grid = 1;
   forward_step_kernel<<<grid, SOLVE_THREADS, 0, s>>> (c->A, c->ld, pc.lrow0, pc.row0, pc.h, c->n,
