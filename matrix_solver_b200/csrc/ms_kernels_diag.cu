@@ -280,7 +280,7 @@ ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_ou
 // keeps its column in registers (right-looking: after x_i, rows k > i lose R_ik x_i — 63 independent
 // FMAs, so the kernel runs at DFMA issue rate).  Loads/stores are coalesced across the warp (adjacent
 // threads = adjacent columns): 16 B of HBM traffic per element + 8 B for the panel-buffer copy.
-__global__ void __launch_bounds__ (128, 3)
+__global__ void __launch_bounds__ (128, 2)
 trsm_panel_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restrict__ rows, size_t ld, int h, size_t col_lo,
                    size_t n, const double *__restrict__ dpiece, double *__restrict__ PB, size_t pb_H, size_t pb_k0)
 {
@@ -288,6 +288,16 @@ trsm_panel_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restri
   constexpr int RS = MS_SUB + 2;  // row stride: even (16-byte loads) and not a multiple of 32 banks
   __shared__ __align__ (16) double RT[MS_SUB * RS];
   __shared__ double rinv[MS_SUB], ds[MS_SUB];
+  extern __shared__ double As[];  // [MS_SUB][128]: the CTA's slab of the block row
+  const size_t j0 = col_lo + (size_t)blockIdx.x * 128;
+  // stage the slab first: every thread has its 64 loads in flight at once (the serial solve below
+  // would otherwise wait one HBM round trip per row)
+#pragma unroll 16
+  for (int k = 0; k < MS_SUB; k++)
+    {
+      const size_t j = j0 + threadIdx.x;
+      As[k * 128 + threadIdx.x] = (k < h && j < n) ? rows[(size_t)k * ld + j] : 0.0;
+    }
   for (int e = threadIdx.x; e < MS_SUB * MS_SUB; e += 128)
     {
       const int k = e >> 6, i = e & 63;  // coalesced read of row k of R
@@ -300,19 +310,15 @@ trsm_panel_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restri
       ds[i] = i < h ? dpiece[i] : 1.0;
     }
   __syncthreads ();
-  const size_t j = col_lo + (size_t)blockIdx.x * 128 + threadIdx.x;
+  const size_t j = j0 + threadIdx.x;
   if (j >= n)
     return;
   double x[MS_SUB];
   double *pcol = rows + j;
   double *ppb = PB + chunk_major_index (pb_k0, j, pb_H);
-  double a_next = rows[j];
 #pragma unroll
   for (int i = 0; i < MS_SUB; i++)
     {
-      const double a_i = a_next;
-      if (i + 1 < MS_SUB)
-        a_next = (i + 1 < h) ? pcol[(size_t)(i + 1) * ld] : 0.0;  // prefetch the next row's entry
       // four interleaved partial sums keep four independent FMA chains in flight
       double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
@@ -328,7 +334,7 @@ trsm_panel_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restri
 #pragma unroll
       for (int k = (i & ~3); k < i; k++)
         p0 = fma (RT[i * RS + k], x[k], p0);
-      const double xi = (a_i - ((p0 + p1) + (p2 + p3))) * rinv[i];
+      const double xi = (As[i * 128 + threadIdx.x] - ((p0 + p1) + (p2 + p3))) * rinv[i];
       x[i] = xi;
       if (i < h)
         {
@@ -347,7 +353,14 @@ ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t
     return MS_OK;
   MS_CHECK_ARG (h >= 1 && h <= MS_SUB, "trsm panel piece must have 1..64 rows");
   unsigned grid = (unsigned)((n - col_lo + 127) / 128);
-  trsm_panel_kernel<<<grid, 128, 0, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H, pb_k0);
+  const size_t smem = (size_t)MS_SUB * 128 * sizeof (double);
+  static bool configured = false;
+  if (!configured)
+    {
+      MS_CUDA (cudaFuncSetAttribute (trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+  trsm_panel_kernel<<<grid, 128, smem, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H, pb_k0);
   LAUNCH_COUNT (c);
   MS_CUDA (cudaGetLastError ());
   return MS_OK;
