@@ -246,11 +246,9 @@ int ms_k_packed_rows (ms_ctx *c, double *d_seg, size_t J, size_t w, size_t i0, s
 int ms_k_get_col (ms_ctx *c, size_t j, double *d_out, cudaStream_t s);
 int ms_k_norms (ms_ctx *c, const double *r, const double *x, size_t n, double *d_out2,
                 cudaStream_t s);
-int ms_k_zero (ms_ctx *c, double *p, size_t cnt, cudaStream_t s);
 int ms_k_axpy_minus (ms_ctx *c, double *r, const double *b, size_t n, cudaStream_t s);
 
 // ms_kernels_diag.cu
-int ms_k_pretest (ms_ctx *c, const double *blk, size_t ld, int h, double thresh, cudaStream_t s);
 int ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_out,
                double *wt_out, double *inv_out, const double *pre_diag, size_t pre_ld, int pre_count,
                cudaStream_t s);

@@ -18,27 +18,11 @@
 // uses the _rn intrinsics so that nvcc cannot contract a*b-c into an FMA.
 //
 // The reference tests the not-yet-updated a_ii first (src/solver.cpp:117); that "pre" test
-// runs for a whole block row in pretest_kernel before any piece of it is touched.
+// runs for a whole block row at the top of the diag kernel of its first piece, before any piece
+// of the block row is touched.
 #include "ms_common.cuh"
 
 #define LAUNCH_COUNT(c) ((c)->stats.kernel_launches++)
-
-__global__ void __launch_bounds__ (256)
-pretest_kernel (const double *__restrict__ blk, size_t ld, int h, double thresh, int *flags)
-{
-  for (int i = threadIdx.x; i < h; i += 256)
-    if (fabs (blk[(size_t)i * ld + i]) < thresh)
-      flags[0] = 1;
-}
-
-int
-ms_k_pretest (ms_ctx *c, const double *blk, size_t ld, int h, double thresh, cudaStream_t s)
-{
-  pretest_kernel<<<1, 256, 0, s>>> (blk, ld, h, thresh, c->flags);
-  LAUNCH_COUNT (c);
-  MS_CUDA (cudaGetLastError ());
-  return MS_OK;
-}
 
 // dynamic smem: a[h][h+1] | v[h][h+1] | rdiag[h] | dd[h]
 //

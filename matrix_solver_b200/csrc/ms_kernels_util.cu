@@ -367,14 +367,6 @@ ms_k_norms (ms_ctx *c, const double *r, const double *x, size_t n, double *d_out
   return MS_OK;
 }
 
-int
-ms_k_zero (ms_ctx *c, double *p, size_t cnt, cudaStream_t s)
-{
-  (void)c;
-  MS_CUDA (cudaMemsetAsync (p, 0, cnt * sizeof (double), s));
-  return MS_OK;
-}
-
 // ----------------------------------------------------------------------------- K11 uploads
 // d_rows holds nrows full host rows (ld_src apart) starting at global row row0; keep j >= start
 // of the diagonal block for the rows this rank owns.
