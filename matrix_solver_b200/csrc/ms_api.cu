@@ -123,6 +123,7 @@ ctx_free (ms_ctx *c)
     cudaFree (c->vec[i]);
   cudaFree (c->acc);
   cudaFree (c->scratch);
+  cudaFree (c->sweep_ready);
   cudaFree (c->flags);
   cudaFree (c->d_stage);
   if (c->h_flags)
@@ -251,6 +252,9 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   const char *e = getenv ("MS_FORCE_GENERIC");
   if (e && atoi (e))
     c->force_generic = true;
+  e = getenv ("MS_NO_SWEEP");
+  if (e && atoi (e))
+    c->no_sweep = true;
   e = getenv ("MS_PANEL_GEMM");
   if (e && atoi (e))
     c->panel_trsm = false;
@@ -279,6 +283,8 @@ ms_set_option (ms_ctx *c, const char *key, long value)
     c->profile_update = value != 0;
   else if (!strcmp (key, "panel_trsm"))
     c->panel_trsm = value != 0;
+  else if (!strcmp (key, "single_launch_sweeps"))
+    c->no_sweep = value == 0;
   else
     {
       ms_set_error ("unknown option %s", key);
@@ -904,7 +910,9 @@ ms_solve_forward (ms_ctx *c, double norma)
   MS_CUDA (cudaMemsetAsync (c->acc, 0, (c->ld + MS_SUB) * sizeof (double), s));
   if (c->nranks > 1)
     MS_CUDA (cudaMemsetAsync (c->vec[MS_VEC_Y], 0, c->ld * sizeof (double), s));
-  for (size_t I = 0; I < c->nblocks; I++)
+  int swept = 0;
+  MS_TRY (ms_k_sweep (c, true, thresh, s, &swept));
+  for (size_t I = 0; I < c->nblocks && !swept; I++)
     {
       int owner = c->owner_of_block (I);
       if (c->nranks > 1)
@@ -934,7 +942,9 @@ ms_solve_backward (ms_ctx *c, double norma)
   phase_timer t (c, &c->stats.backward_ms);
   MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), s));
   MS_CUDA (cudaMemsetAsync (c->acc, 0, (c->ld + MS_SUB) * sizeof (double), s));
-  for (size_t I = c->nblocks; I-- > 0;)
+  int swept = 0;
+  MS_TRY (ms_k_sweep (c, false, thresh, s, &swept));
+  for (size_t I = c->nblocks; !swept && I-- > 0;)
     {
       int owner = c->owner_of_block (I);
       // local rows strictly above block row I on this rank

@@ -115,6 +115,9 @@ struct ms_ctx
   std::vector<ms_piece> pieces;
   std::vector<size_t> block_first_piece;  // index into pieces, size nblocks+1
 
+  int *sweep_ready = nullptr;  // epoch flags of the single-launch sweeps
+  int sweep_epoch = 0;
+  bool no_sweep = false;       // MS_NO_SWEEP=1: per-piece solve launches
   void *nccl = nullptr;  // ncclComm_t when nranks > 1
   void *p2p = nullptr;   // copy-engine panel transport (ms_p2p.cu) when nranks > 1
 
@@ -274,6 +277,7 @@ int ms_k_generic_block_update (ms_ctx *c, double *A, size_t lda, const double *R
 int ms_k_forward_step (ms_ctx *c, const ms_piece &pc, double thresh, cudaStream_t s);
 int ms_k_backward_step (ms_ctx *c, const ms_piece &pc, size_t lrows_above, double thresh,
                         cudaStream_t s);
+int ms_k_sweep (ms_ctx *c, bool forward, double thresh, cudaStream_t s, int *done);
 
 enum { MS_MODE_UPDATE = 0, MS_MODE_PANEL = 1 };
 enum { MS_SYM_BNORM = 0, MS_SYM_SYMV = 1 };

@@ -15,6 +15,10 @@
 //       R_kt x_t to acc_k for its slice of rows k < r0 (the column block above the piece).
 // With several ranks the owner's acc is completed by a reduction before the step (ms_api.cu).
 // The pivot tests |R_jj| < EPS*norm of :195-199 and :232-236 raise flags[0].
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "ms_common.cuh"
 
 #define LAUNCH_COUNT(c) ((c)->stats.kernel_launches++)
@@ -207,5 +211,305 @@ ms_k_backward_step (ms_ctx *c, const ms_piece &pc, size_t lrows_above, double th
                                                      thresh, c->flags);
   LAUNCH_COUNT (c);
   MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
+// ============================================================================ single-launch sweeps
+// One cooperative launch per sweep (single GPU, m % 64 == 0): G co-resident CTAs, 64-wide chunk c of
+// the unknowns belongs to CTA c % G, which keeps that chunk's accumulator in shared memory.
+//   forward, piece t (rows 64t..): the owner of chunk t solves R_tt^T y_t = b_t - acc_t, publishes
+//   y_t (global memory + release flag); every CTA then applies rows t to the chunks it owns (> t).
+//   The chunk on the critical path (t+1) is updated and solved FIRST, before the CTA's other chunks.
+//   backward is the mirror image over row chunks (x_t published, rows above updated).
+// Each element of R is read once, 512-byte coalesced segments, 16 loads in flight per thread.
+// Flags are epochs, never reset.  All CTAs spin on flags written by other CTAs of the SAME launch,
+// which is why the launch is cooperative (co-residency guaranteed).
+namespace cg = cooperative_groups;
+
+constexpr int SWEEP_MAX_SLOTS = 24;  // chunks one CTA may own: ceil(T / G)
+
+struct sweep_args
+{
+  const double *A;
+  size_t ld, n;
+  const double *b;     // forward: b ; backward: y
+  const double *d;     // backward only
+  double *out;         // forward: y ; backward: x
+  int *ready;          // T flags
+  int epoch;
+  int T;               // number of 64-row pieces
+  double thresh;
+  int *flags;
+};
+
+__device__ __forceinline__ void
+sweep_wait (const int *flag, int epoch)
+{
+  if (threadIdx.x == 0)
+    {
+      int v;
+      do
+        {
+          asm volatile ("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          if (v != epoch)
+            __nanosleep (40);
+        }
+      while (v != epoch);
+    }
+  __syncthreads ();
+}
+
+__device__ __forceinline__ void
+sweep_publish (int *flag, int epoch)
+{
+  __threadfence ();
+  __syncthreads ();
+  if (threadIdx.x == 0)
+    asm volatile ("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+
+// 64 x 64 block update shared by both sweeps, split in two so that the loads can be issued before
+// the vector they are multiplied with is known (critical path: the neighbour chunk).
+// FORWARD : accs[j] += sum_i A(r0 + i, c0 + j) * v[i]   (column sums; thread = column x 16-row group)
+// BACKWARD: accs[i] += sum_j A(r0 + i, c0 + j) * v[j]   (row sums;    thread = row x 16-col group)
+template <bool FORWARD>
+__device__ __forceinline__ void
+sweep_block_load (const sweep_args &sa, size_t r0, int hr, size_t c0, int hc, double (&t)[16])
+{
+  if (FORWARD)
+    {
+      const int cx = threadIdx.x & 63, rg = threadIdx.x >> 6;
+      const double *col = sa.A + (r0 + (size_t)rg * 16) * sa.ld + c0 + cx;
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        t[i] = (cx < hc && rg * 16 + i < hr) ? __ldcs (col + (size_t)i * sa.ld) : 0.0;
+    }
+  else
+    {
+      const int row = threadIdx.x >> 2, cgp = threadIdx.x & 3;
+      const double *rp = sa.A + (r0 + row) * sa.ld + c0 + cgp * 16;
+#pragma unroll
+      for (int j = 0; j < 16; j++)
+        t[j] = (row < hr && cgp * 16 + j < hc) ? __ldcs (rp + j) : 0.0;
+    }
+}
+
+template <bool FORWARD>
+__device__ __forceinline__ void
+sweep_block_apply (const double (&t)[16], const double *v, double *accs, double (*part)[64])
+{
+  double s = 0.0;
+  if (FORWARD)
+    {
+      const int cx = threadIdx.x & 63, rg = threadIdx.x >> 6;
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        s += t[i] * v[rg * 16 + i];
+      part[rg][cx] = s;
+      __syncthreads ();
+      if (threadIdx.x < 64)
+        accs[threadIdx.x] += (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
+      __syncthreads ();
+    }
+  else
+    {
+      const int row = threadIdx.x >> 2, cgp = threadIdx.x & 3;
+#pragma unroll
+      for (int j = 0; j < 16; j++)
+        s += t[j] * v[cgp * 16 + j];
+      s += __shfl_xor_sync (0xffffffffu, s, 1);
+      s += __shfl_xor_sync (0xffffffffu, s, 2);
+      if (cgp == 0)
+        accs[row] += s;
+      __syncthreads ();
+    }
+}
+
+template <bool FORWARD>
+__device__ __forceinline__ void
+sweep_block_update (const sweep_args &sa, size_t r0, int hr, size_t c0, int hc, const double *v, double *accs,
+                    double (*part)[64])
+{
+  double t[16];
+  sweep_block_load<FORWARD> (sa, r0, hr, c0, hc, t);
+  sweep_block_apply<FORWARD> (t, v, accs, part);
+}
+
+template <bool FORWARD>
+__global__ void __launch_bounds__ (256)
+sweep_kernel (const sweep_args sa)
+{
+  __shared__ double Rs[64 * 65];
+  __shared__ double vs[64];               // y_t resp. x_t of the current piece
+  __shared__ double accs[SWEEP_MAX_SLOTS][64];
+  __shared__ double part[4][64];
+  const int G = gridDim.x, me = blockIdx.x, T = sa.T;
+  for (int e = threadIdx.x; e < SWEEP_MAX_SLOTS * 64; e += 256)
+    (&accs[0][0])[e] = 0.0;
+  __syncthreads ();
+
+  auto piece_h = [&] (int t) { return (int)min ((size_t)64, sa.n - (size_t)t * 64); };
+  auto slot_of = [&] (int c) { return c / G; };
+
+  // diagonal block of piece t -> Rs: 16 independent loads per thread, then the stores
+  auto load_diag = [&] (int t) {
+    const int h = piece_h (t);
+    const size_t r0 = (size_t)t * 64;
+    double r[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++)
+      {
+        const int e = threadIdx.x + 256 * u, i = e >> 6, j = e & 63;
+        r[u] = (i < h && j < h && j >= i) ? sa.A[(r0 + i) * sa.ld + r0 + j] : 0.0;
+      }
+#pragma unroll
+    for (int u = 0; u < 16; u++)
+      {
+        const int e = threadIdx.x + 256 * u, i = e >> 6, j = e & 63;
+        Rs[i * 65 + j] = r[u];
+      }
+  };
+
+  // solve piece t (this CTA owns chunk t and its accumulator is complete) and publish the result
+  auto solve_and_publish = [&] (int t, bool diag_loaded) {
+    const int h = piece_h (t);
+    const size_t r0 = (size_t)t * 64;
+    if (!diag_loaded)
+      load_diag (t);
+    if (threadIdx.x < 64)
+      {
+        double rhs = 0.0;
+        if (threadIdx.x < h)
+          rhs = FORWARD ? sa.b[r0 + threadIdx.x] - accs[slot_of (t)][threadIdx.x]
+                        : sa.d[r0 + threadIdx.x] * sa.b[r0 + threadIdx.x] - accs[slot_of (t)][threadIdx.x];
+        vs[threadIdx.x] = rhs;
+      }
+    __syncthreads ();
+    if (threadIdx.x < 32)
+      warp_tri_solve<FORWARD> (Rs, vs, h, sa.thresh, sa.flags);
+    __syncthreads ();
+    if (threadIdx.x < h)
+      sa.out[r0 + threadIdx.x] = vs[threadIdx.x];
+    sweep_publish (sa.ready + t, sa.epoch);
+  };
+
+  bool solved_ahead = false;  // the piece of this iteration was already solved in the previous one
+  for (int step = 0; step < T; step++)
+    {
+      const int t = FORWARD ? step : T - 1 - step;
+      const int h = piece_h (t);
+      const size_t r0 = (size_t)t * 64;
+      const int tn = FORWARD ? t + 1 : t - 1;
+      const bool own_next = tn >= 0 && tn < T && tn % G == me;
+      const bool ahead = own_next && G > 1;  // this CTA is on the critical path of piece tn
+      double pre[16];
+      if (ahead)
+        {
+          // everything that does not depend on piece t's solution is fetched before we wait for it
+          load_diag (tn);
+          if (FORWARD)
+            sweep_block_load<true> (sa, r0, h, (size_t)tn * 64, piece_h (tn), pre);
+          else
+            sweep_block_load<false> (sa, (size_t)tn * 64, piece_h (tn), r0, h, pre);
+        }
+      if (t % G == me)
+        {
+          if (!solved_ahead)
+            solve_and_publish (t, false);
+          // vs holds the solution of piece t
+        }
+      else
+        {
+          sweep_wait (sa.ready + t, sa.epoch);
+          if (threadIdx.x < 64)
+            vs[threadIdx.x] = threadIdx.x < h ? __ldcg (sa.out + r0 + threadIdx.x) : 0.0;
+          __syncthreads ();
+        }
+      solved_ahead = false;
+      if (ahead)
+        {
+          // neighbour chunk first: finish its accumulator, solve it, publish; then catch up
+          sweep_block_apply<FORWARD> (pre, vs, accs[slot_of (tn)], part);
+          double vkeep = 0.0, vnext = 0.0;
+          if (threadIdx.x < 64)
+            vkeep = vs[threadIdx.x];
+          __syncthreads ();
+          solve_and_publish (tn, true);
+          solved_ahead = true;
+          if (threadIdx.x < 64)
+            {
+              vnext = vs[threadIdx.x];
+              vs[threadIdx.x] = vkeep;
+            }
+          __syncthreads ();
+          if (FORWARD)
+            for (int c = tn + G; c < T; c += G)
+              sweep_block_update<true> (sa, r0, h, (size_t)c * 64, piece_h (c), vs, accs[slot_of (c)], part);
+          else
+            for (int c = tn - G; c >= 0; c -= G)
+              sweep_block_update<false> (sa, (size_t)c * 64, 64, r0, h, vs, accs[slot_of (c)], part);
+          if (threadIdx.x < 64)
+            vs[threadIdx.x] = vnext;
+          __syncthreads ();
+        }
+      else if (FORWARD)
+        {
+          int c = G == 1 ? t + 1 : t + 1 + ((me - (t + 1)) % G + G) % G;  // first chunk > t owned by me
+          for (; c < T; c += G)
+            sweep_block_update<true> (sa, r0, h, (size_t)c * 64, piece_h (c), vs, accs[slot_of (c)], part);
+        }
+      else
+        {
+          int c = G == 1 ? t - 1 : t - 1 - (((t - 1) - me) % G + G) % G;  // last chunk < t owned by me
+          for (; c >= 0; c -= G)
+            sweep_block_update<false> (sa, (size_t)c * 64, 64, r0, h, vs, accs[slot_of (c)], part);
+        }
+    }
+}
+
+// returns MS_OK and sets *done = 1 when the single-launch sweep ran, *done = 0 when the caller has to
+// fall back to the per-piece launches (several ranks, m % 64 != 0, or too many chunks per CTA)
+int
+ms_k_sweep (ms_ctx *c, bool forward, double thresh, cudaStream_t s, int *done)
+{
+  *done = 0;
+  if (c->nranks != 1 || c->m % MS_SUB != 0 || c->no_sweep)
+    return MS_OK;
+  const int T = (int)((c->n + 63) / 64);
+  static int max_per_sm = -1;
+  if (max_per_sm < 0)
+    {
+      int a = 0, b = 0;
+      MS_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&a, sweep_kernel<true>, 256, 0));
+      MS_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b, sweep_kernel<false>, 256, 0));
+      max_per_sm = std::max (1, std::min (std::min (a, b), 4));
+    }
+  int G = std::min (T, max_per_sm * c->sm_count);
+  if ((T + G - 1) / G > SWEEP_MAX_SLOTS)
+    return MS_OK;
+  if (!c->sweep_ready)
+    {
+      MS_CUDA (cudaMalloc (&c->sweep_ready, ((size_t)T + 8) * sizeof (int)));
+      MS_CUDA (cudaMemsetAsync (c->sweep_ready, 0, ((size_t)T + 8) * sizeof (int), s));
+    }
+  sweep_args sa;
+  sa.A = c->A;
+  sa.ld = c->ld;
+  sa.n = c->n;
+  sa.b = forward ? c->vec[MS_VEC_B] : c->vec[MS_VEC_Y];
+  sa.d = c->vec[MS_VEC_D];
+  sa.out = forward ? c->vec[MS_VEC_Y] : c->vec[MS_VEC_X];
+  sa.ready = c->sweep_ready;
+  sa.epoch = ++c->sweep_epoch;
+  sa.T = T;
+  sa.thresh = thresh;
+  sa.flags = c->flags;
+  void *args[] = {(void *)&sa};
+  if (forward)
+    MS_CUDA (cudaLaunchCooperativeKernel ((void *)sweep_kernel<true>, dim3 (G), dim3 (256), args, 0, s));
+  else
+    MS_CUDA (cudaLaunchCooperativeKernel ((void *)sweep_kernel<false>, dim3 (G), dim3 (256), args, 0, s));
+  LAUNCH_COUNT (c);
+  *done = 1;
   return MS_OK;
 }
