@@ -247,7 +247,16 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
         return fail (r);
       r = ms_p2p_init (c);
       if (r < 0)
-        return fail (r);
+        {
+          // peer mapping unavailable (no CUDA IPC between these processes, no peer access ...):
+          // keep going with the NCCL broadcast unless the transport was requested explicitly
+          const char *force = getenv ("MS_P2P");
+          if (force && atoi (force))
+            return fail (r);
+          fprintf (stderr, "matrix_solver_b200: peer-memory panel transport unavailable (%s); using ncclBroadcast\n",
+                   ms_last_error ());
+          ms_p2p_destroy (c);
+        }
     }
   const char *e = getenv ("MS_FORCE_GENERIC");
   if (e && atoi (e))

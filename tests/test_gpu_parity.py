@@ -229,7 +229,8 @@ def test_pipeline_against_oracle_formula_sweep(ms, ora, n, m):
 
 
 @pytest.mark.parametrize("opts", [(("force_generic", 1),), (("lookahead", 0),), (("force_generic", 1), ("lookahead", 0)),
-                                  (("panel_trsm", 0),), (("panel_trsm", 0), ("force_generic", 1))])
+                                  (("panel_trsm", 0),), (("panel_trsm", 0), ("force_generic", 1)),
+                                  (("single_launch_sweeps", 0),)])
 def test_kernel_families_and_schedules_agree(ms, opts):
     """DMMA tiles vs generic DFMA kernel, look-ahead vs in-order: same factor within rounding."""
     n, m = 640, 128
@@ -240,6 +241,25 @@ def test_kernel_families_and_schedules_agree(ms, opts):
     assert rel(alt["x"], base["x"]) <= tol
     if ("lookahead", 0) in opts and ("force_generic", 1) not in opts:
         assert np.array_equal(alt["R"], base["R"])           # scheduling must not change arithmetic
+
+
+def test_hilbert_generator(ms):
+    """The reference's second generator (test/test_mat.cpp:18-22, hilb = 1/(i+j+1)): device generator
+    against numpy, and a solve of the (ill-conditioned) system at a size where it is still SPD in fp64."""
+    n, m = 10, 4
+    with ms.Solver(n, m) as s:
+        s.init_formula(1)
+        a = s.get_upper()
+        i, j = np.indices((n, n))
+        assert np.array_equal(np.triu(a), np.triu(1.0 / (i + j + 1.0)))
+        norm = s.b_and_norm()
+        assert norm == pytest.approx(np.abs(1.0 / (i + j + 1.0)).sum(1).max(), rel=1e-14)
+        fail, _ = s.factor(norm)
+        assert not fail
+        assert not s.solve_forward(norm) and not s.solve_backward(norm)
+        s.init_formula(1)
+        res, err = s.residual()
+        assert res <= 1e-14 * n and err < 1e-2      # cond(H_10) ~ 1.6e13
 
 
 def test_indefinite_and_random_spd_dense(ms, ora):
