@@ -101,9 +101,15 @@ diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *
     }
   __syncthreads ();
 
+#ifdef MS_DIAG_TIMING
+  long long acc_p = 0, acc_u = 0;
+#endif
   for (int i = 0; i + 1 < h; i++)
     {
       const double di = dd[i];
+#ifdef MS_DIAG_TIMING
+      long long tl0 = clock64 ();
+#endif
       if (tid < 32)
         {
           // pivot warp: row i+1 <- row i+1 - (r_{i,i+1} r_{i,j}) d_i, then finish it
@@ -118,6 +124,9 @@ diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *
           for (int j = row + lane + 64; j < h; j += 32)
             a[row * S + j] = __dsub_rn (a[row * S + j], __dmul_rn (__dmul_rn (rk, a[i * S + j]), di));
           finish_row (row, c0, c1);
+#ifdef MS_DIAG_TIMING
+          acc_p += clock64 () - tl0;
+#endif
         }
       else
         {
@@ -158,11 +167,18 @@ diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *
                 if (k < h && j < h && j >= k)
                   a[k * S + j] = c[u][w];
               }
+#ifdef MS_DIAG_TIMING
+          acc_u += clock64 () - tl0;
+#endif
         }
       __syncthreads ();
     }
 #ifdef MS_DIAG_TIMING
   long long tc2 = clock64 ();
+  if (tid == 0)
+    flags[2] = (int)acc_p;
+  if (tid == 255)
+    flags[3] = (int)acc_u;
 #endif
 
   // ---- K2: inverse, one thread per column, rows bottom-up, k ascending

@@ -14,4 +14,4 @@ for w in (16, 32, 64, 96):
         ms.block_diag_factor(np.triu(spd), np.abs(spd).sum(1).max())
     buf=(ctypes.c_int*8)()
     L.ms_debug_blk_flags(buf)
-    print(w, "cycles load/factor/inverse/writeback:", list(buf)[4:8])
+    print(w, "cycles load/factor/inverse/writeback:", list(buf)[4:8], "pivot-warp busy / update-warp busy:", list(buf)[2:4])
