@@ -286,47 +286,52 @@ def our_arm(args):
     # ---- e2e: host buffers in, host results out (rows of A from page-locked memory)
     e2e = None
     if not args.no_e2e:
-        rows_mine = layout.rows_local(n, m, rank, world)
-        # every rank keeps the rows it owns, full length, contiguous in block-row order
-        pin = ms.PinnedBuffer(max(rows_mine, 1) * n)
-        blocks = [I for I in range(rank, layout.n_blocks(n, m), world)]
-        solver.init_formula(0)
-        off = 0
-        for I in blocks:
-            h = layout.block_rows(n, m, I)
-            # write block row I so that global column j sits at offset j of each row
-            solver.download_rows_ptr(pin.ptr.value + off * n * 8, I * m, h, n)
-            off += h
-        sync_all()
-        e2e_times = []
-        h2d0, d2h0 = solver.stats()["h2d_bytes"], solver.stats()["d2h_bytes"]
-        for it in range(1 + args.e2e_steps):
-            sync_all()
-            t1 = time.perf_counter()
+        try:
+            rows_mine = layout.rows_local(n, m, rank, world)
+            # every rank keeps the rows it owns, full length, contiguous in block-row order
+            pin = ms.PinnedBuffer(max(rows_mine, 1) * n)
+            blocks = [I for I in range(rank, layout.n_blocks(n, m), world)]
+            solver.init_formula(0)
             off = 0
             for I in blocks:
                 h = layout.block_rows(n, m, I)
-                solver.upload_rows_ptr(pin.ptr.value + off * n * 8, I * m, h, n)
+                # write block row I so that global column j sits at offset j of each row
+                solver.download_rows_ptr(pin.ptr.value + off * n * 8, I * m, h, n)
                 off += h
-            nrm = solver.b_and_norm()
-            solver.factor(nrm)
-            solver.solve_forward(nrm)
-            solver.solve_backward(nrm)
-            x = solver.get_vec("x")
-            d = solver.get_vec("d")
             sync_all()
-            if it > 0:
-                e2e_times.append(time.perf_counter() - t1)
-            else:
-                h2d0, d2h0 = solver.stats()["h2d_bytes"], solver.stats()["d2h_bytes"]
-        t_e2e = dist.max_over_ranks(sum(e2e_times) / len(e2e_times))
-        stx = solver.stats()
-        e2e = {"value": layout.factor_flops(n) / t_e2e / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": dist.sum_over_ranks((stx["h2d_bytes"] - h2d0) / len(e2e_times)),
-               "d2h_bytes_per_step": dist.sum_over_ranks((stx["d2h_bytes"] - d2h0) / len(e2e_times)),
-               "seconds": t_e2e, "x_err_vs_planted": float(np.linalg.norm(x - (np.arange(n) % 2 == 0))),
-               "what": "pinned host rows -> ms_upload_rows -> b/norm -> factor -> forward -> backward -> D2H x, d"}
-        pin.free()
+            e2e_times = []
+            h2d0, d2h0 = solver.stats()["h2d_bytes"], solver.stats()["d2h_bytes"]
+            for it in range(1 + args.e2e_steps):
+                sync_all()
+                t1 = time.perf_counter()
+                off = 0
+                for I in blocks:
+                    h = layout.block_rows(n, m, I)
+                    solver.upload_rows_ptr(pin.ptr.value + off * n * 8, I * m, h, n)
+                    off += h
+                nrm = solver.b_and_norm()
+                solver.factor(nrm)
+                solver.solve_forward(nrm)
+                solver.solve_backward(nrm)
+                x = solver.get_vec("x")
+                d = solver.get_vec("d")
+                sync_all()
+                if it > 0:
+                    e2e_times.append(time.perf_counter() - t1)
+                else:
+                    h2d0, d2h0 = solver.stats()["h2d_bytes"], solver.stats()["d2h_bytes"]
+            t_e2e = dist.max_over_ranks(sum(e2e_times) / len(e2e_times))
+            stx = solver.stats()
+            e2e = {"value": layout.factor_flops(n) / t_e2e / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": dist.sum_over_ranks((stx["h2d_bytes"] - h2d0) / len(e2e_times)),
+                   "d2h_bytes_per_step": dist.sum_over_ranks((stx["d2h_bytes"] - d2h0) / len(e2e_times)),
+                   "seconds": t_e2e, "x_err_vs_planted": float(np.linalg.norm(x - (np.arange(n) % 2 == 0))),
+                   "what": "pinned host rows -> ms_upload_rows -> b/norm -> factor -> forward -> backward -> D2H x, d"}
+            pin.free()
+
+        except (ms.MSError, MemoryError) as exc:  # e.g. not enough page-lockable host memory
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "error": str(exc)[:200]}
 
     solver.close()
     if rank != 0:
