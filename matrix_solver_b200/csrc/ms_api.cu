@@ -795,6 +795,8 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
       // panel stream overwrites it (by factoring or by receiving the broadcast)
       if (la && I >= MS_NPB)
         MS_CUDA (cudaStreamWaitEvent (sp, ev_free[I - MS_NPB], 0));
+      if (p2p)
+        MS_TRY (ms_p2p_before_overwrite (c, I, sp));
       if (owner == c->rank)
         {
           if (la && I > 0)
