@@ -232,7 +232,7 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   CK (cudaStreamCreateWithPriority (&c->s_row, cudaStreamNonBlocking, hi));
   CK (cudaEventCreate (&c->ev_t0));
   CK (cudaEventCreate (&c->ev_t1));
-  c->ev_pool.resize (4 * c->nblocks + 8);
+  c->ev_pool.resize (5 * c->nblocks + 10);
   c->trace = getenv ("MS_TRACE") && atoi (getenv ("MS_TRACE"));
   for (auto &e : c->ev_pool)
     CK (cudaEventCreateWithFlags (&e, c->trace ? cudaEventDefault : cudaEventDisableTiming));
@@ -678,7 +678,7 @@ do_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_end, int 
 }
 
 static int
-factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s)
+factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s, cudaEvent_t rest_ready)
 {
   const size_t rowsI = c->block_rows (I);
   const size_t lrowI = (I / (size_t)c->nranks) * c->m;
@@ -724,9 +724,12 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s)
                                           c->n, s));
             }
         }
-      // later pieces of the same block row
+      // later pieces of the same block row (their rows must have received the previous panel: the
+      // first piece was updated ahead of them so that its diag/TRSM could start early)
       size_t lr_next = pc.lrow0 + (size_t)pc.h;
       size_t lr_end = lrowI + rowsI;
+      if (rest_ready && first && lr_next < lr_end)
+        MS_CUDA (cudaStreamWaitEvent (s, rest_ready, 0));
       MS_TRY (do_update (c, pb, I, lr_next, lr_end, pc.h, k0, s, false));
     }
   return MS_OK;
@@ -765,6 +768,7 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
   cudaEvent_t *ev_strip = ev_panel + nb + 2;              // block row I updated through panel I-1
   cudaEvent_t *ev_u2a = ev_strip + nb + 2;                // block row I updated through panel I-2
   cudaEvent_t *ev_free = ev_u2a + nb + 2;                 // main stream is done with panel I
+  cudaEvent_t *ev_rest = ev_free + nb + 2;                // pieces 1.. of block row I updated through panel I-1
   if (la)
     {
       MS_CUDA (cudaEventRecord (ev_strip[0], sm));
@@ -801,7 +805,7 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
         {
           if (la && I > 0)
             MS_CUDA (cudaStreamWaitEvent (sp, ev_strip[I], 0));
-          MS_TRY (factor_block_row (c, I, pb, thresh, sp));
+          MS_TRY (factor_block_row (c, I, pb, thresh, sp, (la && I > 0) ? ev_rest[I] : nullptr));
         }
       if (P > 1 && !p2p)
         MS_TRY (ms_nccl_bcast_panel (c, I, pb, owner, sp));
@@ -824,10 +828,17 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
               if (I >= 1)
                 MS_CUDA (cudaStreamWaitEvent (su, ev_u2a[I + 1], 0));
             }
+          // first piece of block row I+1 first: its diag kernel is the head of the next panel chain
           size_t lr = lrow_of_block (I + 1);
-          MS_TRY (timed (su, I, pb, lr, lr + c->block_rows (I + 1)));
+          size_t lr_end = lr + c->block_rows (I + 1);
+          size_t lr_p0 = std::min (lr + (size_t)MS_SUB, lr_end);
+          MS_TRY (timed (su, I, pb, lr, lr_p0));
           if (la)
             MS_CUDA (cudaEventRecord (ev_strip[I + 1], su));
+          if (lr_p0 < lr_end)
+            MS_TRY (timed (su, I, pb, lr_p0, lr_end));
+          if (la)
+            MS_CUDA (cudaEventRecord (ev_rest[I + 1], su));
         }
       // U2a: block row I+2 (the next U1 depends on it), then U2b: the rest
       size_t lr_rest;
