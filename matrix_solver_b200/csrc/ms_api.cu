@@ -174,7 +174,7 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   c->nblocks = n / m + (n % m > 0);
   c->ld = round_up (n, MS_CHUNK);
   c->hpb = round_up (m, MS_SUB);
-  c->fast = (m % MS_SUB == 0);
+  c->fast = (m % MS_SUB == 0 && m <= 1024);  // the tile kernel keeps K = m sign words in shared memory
   c->rows_local = 0;
   for (size_t I = rank; I < c->nblocks; I += (size_t)nranks)
     c->rows_local += c->block_rows (I);

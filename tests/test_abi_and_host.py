@@ -102,3 +102,23 @@ def test_update_flops_close_to_n_cubed_over_three():
     n, m = 8192, 256
     assert abs(layout.update_flops(n, m) / layout.factor_flops(n) - 1) < 0.06
     assert sum(layout.update_flops(n, m, r, 4) for r in range(4)) == pytest.approx(layout.update_flops(n, m))
+
+
+def test_rank_runtime_forks_and_barriers(tmp_path):
+    """The CLI's replacement for `mpirun -np P`: MS_NGPU=P forks P ranks before CUDA is touched
+    (host/ms_rt.cpp).  Rank numbering, barriers and the join are exercised here without a GPU."""
+    _ensure_lib()
+    exe = tmp_path / "rt_ranks_test"
+    host = os.path.join(ROOT, "matrix_solver_b200", "host")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + host, "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "rt_ranks_test.cpp"), os.path.join(host, "ms_rt.cpp"),
+                    "-L" + os.path.dirname(ms.lib_path()), "-lms_b200",
+                    "-Wl,-rpath," + os.path.dirname(ms.lib_path()), "-o", str(exe)], check=True)
+    for p in (1, 3, 4):
+        out = subprocess.run([str(exe)], env=dict(os.environ, MS_NGPU=str(p)), capture_output=True, text=True,
+                             timeout=120)
+        assert out.returncode == 0, out.stderr
+        lines = out.stdout.strip().split("\n")
+        assert lines[-1] == f"rank 0 done, size {p}"
+        rounds = [ln for ln in lines if ln.startswith("round")]
+        assert rounds == [f"round {r} by rank {r % p} of {p}" for r in range(50)]
