@@ -46,8 +46,9 @@ enum { MS_FORMULA_F1 = 0, MS_FORMULA_HILBERT = 1 };
 typedef struct ms_stats
 {
   double factor_ms;       /* device time of the last ms_factor (CUDA events) */
-  double update_ms;       /* summed device time of trailing-update launches (0 unless
-                             ms_set_option(ctx, "profile_update", 1)) */
+  double update_ms;       /* summed device time of the rank-m trailing-update launches (0 unless
+                             ms_set_option(ctx, "profile_update", 1)); with look-ahead two of
+                             them can run concurrently, so the sum over-counts wall time */
   double forward_ms;      /* last ms_solve_forward */
   double backward_ms;     /* last ms_solve_backward */
   double init_ms;         /* last ms_init_formula / upload */
@@ -66,7 +67,11 @@ int ms_device_count (int *count);
 
 /* ---- lifetime (replaces compute_alloc_size + alloc_rows, src/init.cpp:4-58) -- */
 /* rank 0 calls ms_get_unique_id and hands the 128 bytes to every rank by any means
- * (torch.distributed broadcast, a pipe, a file); ignored when nranks == 1. */
+ * (torch.distributed broadcast, a pipe, a file); ignored when nranks == 1.  The id bootstraps an
+ * NCCL communicator (reductions of the solves, b/norm, flags); the factored panels themselves move
+ * over CUDA-IPC peer memory with copy engines unless MS_P2P=0 (then ncclBroadcast).
+ * Options for ms_set_option: "lookahead", "force_generic", "panel_trsm", "single_launch_sweeps",
+ * "profile_update" (0/1). */
 int ms_get_unique_id (void *id128);
 int ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks,
                const void *unique_id);

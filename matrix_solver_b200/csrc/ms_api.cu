@@ -2,13 +2,15 @@
 // right-looking R^T D R factorisation and the two triangular sweeps.
 //
 // Factorisation (replaces the left-looking loop of src/solver.cpp:8-104).  For block row I:
-//   panel stream : pretest (src/solver.cpp:117) -> for every 64-row piece of the block row:
-//                  diag kernel (K1+K2) -> panel kernel (K3: in place + panel buffer) -> update of the
-//                  later pieces of the same block row (K = 64)
-//                  -> [nranks > 1] ncclBroadcast of the panel buffer and of d_I from the owner
-//   main stream  : rank-m update (K4+K5) of block row I+1 first, then of all later block rows.
-// Look-ahead: the panel stream starts block row I+1 as soon as ITS rows have received update I,
-// while the main stream is still applying update I to the rest (two panel buffers alternate).
+//   panel stream : for every 64-row piece of the block row: diag kernel (K1, with the block row's
+//                  pre-update pivot test of src/solver.cpp:117 in its first launch) -> TRSM panel
+//                  kernel (K3: in place + panel buffer) -> update of the later pieces of the same
+//                  block row (K = 64)
+//                  -> [nranks > 1] the panel travels to the peers (ms_p2p.cu, or ncclBroadcast)
+//   row stream   : rank-m update (K4+K5) of block row I+1, its first piece first
+//   main stream  : rank-m update of block row I+2, then of all later block rows.
+// Look-ahead depth 2: the panel stream starts block row I+1 as soon as ITS rows have received update
+// I, while the main stream is still applying updates I-1 and I to the rest (three panel buffers).
 #include <stdarg.h>
 #include <string.h>
 

@@ -16,10 +16,11 @@
 //       minus_RTDRu_l, src/matrix_op.cpp:4-99,156-242):   C -= P^T D P, A and B both slices of
 //       the factored panel P (k = rows of block row I), s_k = d_k.  The diagonal-block (SYRK)
 //       case is just the tile whose row and column ranges coincide.
-//   MS_MODE_PANEL  (K3, reference DRtA / DRtA_l, src/matrix_op.cpp:287-368):   the block row is
-//       overwritten by D V^T A_row, V = inverse of the piece's factor; A = Wt (= V D, emitted by
-//       the diag kernel), B = the piece's rows of the matrix, s_k = 1.  Output also goes to the
-//       panel buffer that feeds the updates / the NCCL broadcast.
+//   MS_MODE_PANEL  (K3 in the reference's own formulation, DRtA / DRtA_l, src/matrix_op.cpp:287-368;
+//       selected with ms_set_option("panel_trsm", 0) — the default K3 is the triangular solve in
+//       ms_kernels_diag.cu):   the block row is overwritten by D V^T A_row, V = inverse of the piece's
+//       factor; A = Wt (= V D, emitted by the diag kernel), B = the piece's rows of the matrix,
+//       s_k = 1.  Output also goes to the panel buffer that feeds the updates and the peers.
 //
 // Fragment mapping (why the shared-memory reads are conflict free) is derived in DESIGN.md
 // "tile kernel"; in short a lane (p = lane/4, q = lane%4) loads with ONE 16-byte LDS the two
