@@ -872,6 +872,7 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
   MS_CUDA (cudaEventSynchronize (c->ev_t1));
   MS_CUDA (cudaStreamSynchronize (c->s_panel));
   MS_CUDA (cudaStreamSynchronize (c->s_row));
+  MS_TRY (ms_p2p_end_factor (c));
   float ms = 0;
   MS_CUDA (cudaEventElapsedTime (&ms, c->ev_t0, c->ev_t1));
   c->stats.factor_ms = ms;

@@ -181,6 +181,21 @@ ms_p2p_destroy (ms_ctx *c)
   c->p2p = nullptr;
 }
 
+// end of a factorisation: drain the flag posts so that none of them can land after the next
+// factorisation (next epoch) has started writing the same words
+int
+ms_p2p_end_factor (ms_ctx *c)
+{
+  p2p_state *p = st (c);
+  if (!p || !p->on)
+    return MS_OK;
+  for (cudaStream_t t : p->s_peer)
+    if (t)
+      MS_CUDA (cudaStreamSynchronize (t));
+  MS_CUDA (cudaStreamSynchronize (p->s_misc));
+  return MS_OK;
+}
+
 void
 ms_p2p_begin_factor (ms_ctx *c)
 {

@@ -22,3 +22,4 @@ int ms_p2p_wait_panel (ms_ctx *c, size_t I, int pb, int owner, cudaStream_t s);
 // every rank, after its main stream is done with panel I (event `freed`)
 int ms_p2p_release_panel (ms_ctx *c, size_t I, cudaEvent_t freed);
 void ms_p2p_begin_factor (ms_ctx *c);
+int ms_p2p_end_factor (ms_ctx *c);

@@ -33,6 +33,8 @@ def main():
     cases = [(4, 3), (30, 9), (100, 48), (130, 64), (200, 64), (512, 64), (1000, 64), (1024, 128), (2048, 256),
              (777, 192), (1500, 100)]
     big = [(8192, 256), (16384, 128), (32768, 256)]
+    if os.environ.get("MS_MULTI_QUICK"):
+        cases, big = cases[::3], [(8192, 256)]
     if os.environ.get("MS_MULTI_BIG"):
         big.append((65536, 256))
     ora = ol.Oracle()
