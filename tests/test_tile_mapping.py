@@ -1,0 +1,127 @@
+"""CPU emulation of the index arithmetic of the DMMA tile kernel (csrc/ms_kernels_tile.cu).
+
+The kernel cannot run here (no GPU), but its correctness rests on three pieces of pure index
+arithmetic that can: the 128-byte TMA swizzle, the lane -> (k-row, column pair) fragment mapping,
+and the epilogue's lane -> (row, 4 contiguous columns) ownership.  This test re-derives them from
+the formulas in the kernel and checks the claims DESIGN.md makes:
+  * every quarter-warp's 16-byte shared-memory loads hit 8 distinct 16-byte slots (no bank conflict);
+  * the fragments fed to mma.sync.m8n8k4.f64 and the epilogue mapping together compute C = A^T B;
+  * the chunk-major panel-buffer index is a bijection and keeps a column range contiguous.
+"""
+import numpy as np
+
+KC, CHUNK, BM, BN = 16, 16, 64, 128
+
+
+def swizzled_byte(k, col):
+    """Where TMA (SWIZZLE_128B, box 16 cols x KC rows of fp64) puts element (k, col) of a chunk."""
+    return k * 128 + (((col // 2) ^ (k & 7)) << 4) + (col % 2) * 8
+
+
+def fragment_offset(lane, g, e):
+    """The kernel's `off`: kr = 8g + 2q + e, off = kr*128 + ((p ^ (kr & 7)) << 4)."""
+    p, q = lane >> 2, lane & 3
+    kr = 8 * g + 2 * q + e
+    return kr, kr * 128 + ((p ^ (kr & 7)) << 4)
+
+
+def test_fragment_loads_are_conflict_free_and_fetch_the_intended_elements():
+    for g in range(KC // 8):
+        for e in range(2):
+            for quarter in range(4):
+                slots = set()
+                for lane in range(8 * quarter, 8 * quarter + 8):
+                    kr, off = fragment_offset(lane, g, e)
+                    slots.add((off // 16) % 8)
+                    p = lane >> 2
+                    # the 16 bytes at `off` are columns 2p and 2p+1 of k-row kr
+                    assert off == swizzled_byte(kr, 2 * p)
+                    assert off + 8 == swizzled_byte(kr, 2 * p + 1)
+                assert len(slots) == 8, (g, e, quarter, slots)
+    # the two interleaved k-sets of a k8 group cover its eight rows exactly once
+    for g in range(KC // 8):
+        rows = sorted(fragment_offset(lane, g, e)[0] for e in range(2) for lane in range(4))
+        assert rows == list(range(8 * g, 8 * g + 8))
+
+
+def dmma_8x8x4(c, a, b):
+    """mma.sync.aligned.m8n8k4.row.col.f64: lane holds a = A[lane>>2][lane&3], b = B[lane&3][lane>>2],
+    c0/c1 = C[lane>>2][(lane&3)*2 + {0,1}]."""
+    A = np.zeros((8, 4))
+    B = np.zeros((4, 8))
+    for lane in range(32):
+        A[lane >> 2, lane & 3] = a[lane]
+        B[lane & 3, lane >> 2] = b[lane]
+    D = A @ B
+    for lane in range(32):
+        for t in range(2):
+            c[lane, t] += D[lane >> 2, (lane & 3) * 2 + t]
+
+
+def test_warp_tile_computes_At_B_through_the_kernel_mappings():
+    rng = np.random.default_rng(0)
+    K = 32
+    PA = rng.standard_normal((K, BM))      # panel columns that match the tile's rows
+    PB = rng.standard_normal((K, BN))      # panel columns that match the tile's columns
+    want = PA.T @ PB
+    got = np.full((BM, BN), np.nan)
+    for warp in range(8):
+        wm, wn = warp >> 2, warp & 3
+        acc = np.zeros((2, 2, 2, 2, 32, 2))          # [ib][jb][a][b][lane][e]
+        for kb in range(K // KC):
+            for g in range(KC // 8):
+                for e in range(2):
+                    fa = np.zeros((2, 32, 2))
+                    fb = np.zeros((2, 32, 2))
+                    for lane in range(32):
+                        p = lane >> 2
+                        kr, _ = fragment_offset(lane, g, e)
+                        k = kb * KC + kr
+                        for ib in range(2):
+                            col = (wm * 2 + ib) * CHUNK + 2 * p
+                            fa[ib, lane] = PA[k, col], PA[k, col + 1]
+                        for jb in range(2):
+                            col = (wn * 2 + jb) * CHUNK + 2 * p
+                            fb[jb, lane] = PB[k, col], PB[k, col + 1]
+                    for ib in range(2):
+                        for jb in range(2):
+                            for a in range(2):
+                                for b in range(2):
+                                    dmma_8x8x4(acc[ib, jb, a, b], fa[ib, :, a], fb[jb, :, b])
+        # epilogue: lane owns row wm*32 + 16*ib + 2p + a, columns wn*32 + 16*jb + 4q + {0,1,2,3}
+        # with values acc[a][b=0][e=0], acc[a][1][0], acc[a][0][1], acc[a][1][1]
+        for lane in range(32):
+            p, q = lane >> 2, lane & 3
+            for ib in range(2):
+                for a in range(2):
+                    r = wm * 32 + 16 * ib + 2 * p + a
+                    for jb in range(2):
+                        c0 = wn * 32 + 16 * jb + 4 * q
+                        vals = [acc[ib, jb, a, 0, lane, 0], acc[ib, jb, a, 1, lane, 0],
+                                acc[ib, jb, a, 0, lane, 1], acc[ib, jb, a, 1, lane, 1]]
+                        for t in range(4):
+                            assert np.isnan(got[r, c0 + t]), "two lanes own the same element"
+                            got[r, c0 + t] = vals[t]
+    assert not np.isnan(got).any(), "some element of the tile is owned by no lane"
+    assert np.allclose(got, want, rtol=1e-13, atol=1e-13)
+
+
+def chunk_major_index(k, j, H):
+    return ((j // CHUNK) * H + k) * CHUNK + (j % CHUNK)
+
+
+def test_chunk_major_panel_buffer_layout():
+    H, ld = 128, 96
+    seen = set()
+    for k in range(H):
+        for j in range(ld):
+            seen.add(chunk_major_index(k, j, H))
+    assert seen == set(range(H * ld))                       # bijection onto the buffer
+    # the columns >= c0 (c0 a multiple of 16) of ALL k rows form one contiguous tail: what one
+    # ncclBroadcast / one peer copy of step I moves
+    c0 = 32
+    tail = sorted(chunk_major_index(k, j, H) for k in range(H) for j in range(c0, ld))
+    assert tail == list(range((c0 // CHUNK) * H * CHUNK, H * ld))
+    # a TMA box (16 columns x 16 k-rows) is one contiguous 2 KB run
+    box = sorted(chunk_major_index(k, j, H) for k in range(16, 32) for j in range(48, 64))
+    assert box == list(range(box[0], box[0] + 256))
