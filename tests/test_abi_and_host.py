@@ -122,3 +122,43 @@ def test_rank_runtime_forks_and_barriers(tmp_path):
         assert lines[-1] == f"rank 0 done, size {p}"
         rounds = [ln for ln in lines if ln.startswith("round")]
         assert rounds == [f"round {r} by rank {r % p} of {p}" for r in range(50)]
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference`: the unmodified reference on the host cores (oracle/_ref) — or the
+    oracle port when _ref was not shipped — reporting the same metric/unit as our arm, plus the
+    cpu_baseline and e2e objects the contract asks for.  Small sample so that it runs in seconds."""
+    import json
+    import sys
+    env = dict(os.environ, MS_BENCH_REF_N="1024")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().split("\n")[-1])
+    assert line["impl"] == "reference"
+    if "unavailable" in line:
+        pytest.skip(line["unavailable"])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["metric"] == "cholesky_factor_gflops_n3_over_3" and line["unit"] == "GFLOP/s"
+    assert line["dtype"] == "f64" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # other ranks of a torchrun launch do nothing and exit 0
+    quiet = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"],
+                           capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), cwd=ROOT)
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
+def test_bench_own_arm_refuses_to_run_without_a_gpu():
+    import json
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert out.returncode != 0
+    assert "no CPU fallback" in json.loads(out.stdout.strip().split("\n")[-1])["error"]
