@@ -28,6 +28,11 @@ C_TOL = 10.0
 @pytest.fixture(scope="module")
 def ms():
     import matrix_solver_b200 as m
+    exe = os.path.join(ol.ROOT, "matrix_solver_b200", "bin", "test_mat")
+    if not os.path.exists(m.lib_path()) or not os.path.exists(exe):
+        # a fresh checkout: build the sm_100a library and the CLI in-tree (the tests may build;
+        # the product never does — it fails loudly when the library is missing)
+        subprocess.run(["make", "-s", "lib", "cli"], cwd=ol.ROOT, check=True)
     if m.device_count() == 0:
         pytest.fail("no CUDA device: the gpu-marked tests must run on a B200 box")
     return m
