@@ -105,6 +105,39 @@ def test_formula_analytic_factor():
     assert o["norm"] == n * (n + 1) / 2
 
 
+def test_oracle_against_numpy_independently():
+    """Independent cross-check: for SPD input R^T R = A is the Cholesky factor
+    numpy computes; for an indefinite matrix with non-zero leading minors R^T D R = A; the two
+    triangular sweeps solve A x = b."""
+    rng = np.random.default_rng(42)
+    for n, m in [(7, 3), (40, 16), (65, 64), (130, 48)]:
+        g = rng.standard_normal((n, n))
+        spd = g @ g.T + n * np.eye(n)
+        a = np.triu(spd)
+        b, norm = ORA.b_norm(a)
+        assert np.allclose(b, spd[:, ::2].sum(1)) and np.isclose(norm, np.abs(spd).sum(1).max())
+        r, d, fail = ORA.factor(a, m, norm)
+        assert not fail and np.all(d == 1.0)
+        assert np.allclose(np.triu(r), np.linalg.cholesky(spd).T, rtol=1e-10, atol=1e-10)
+        y, f2 = ORA.forward(r, b, norm)
+        x, f3 = ORA.backward(r, y, d, norm)
+        assert not f2 and not f3
+        assert np.allclose(x, np.linalg.solve(spd, b), rtol=1e-9, atol=1e-9)
+        # indefinite: flip the sign of a trailing principal block of the SPD matrix's LDL factors
+        L = np.tril(rng.standard_normal((n, n)) * 0.1, -1) + np.eye(n)
+        sign = np.where(np.arange(n) % 4 == 2, -1.0, 1.0)
+        ind = L @ np.diag(sign * (1.0 + rng.random(n))) @ L.T
+        ai = np.triu(ind)
+        bi, normi = ORA.b_norm(ai)
+        ri, di, faili = ORA.factor(ai, m, normi)
+        assert not faili and np.array_equal(di, sign)
+        Ru = np.triu(ri)
+        assert np.allclose(Ru.T @ np.diag(di) @ Ru, ind, rtol=1e-10, atol=1e-10)
+        yi, _ = ORA.forward(ri, bi, normi)
+        xi, _ = ORA.backward(ri, yi, di, normi)
+        assert np.allclose(xi, np.linalg.solve(ind, bi), rtol=1e-8, atol=1e-8)
+
+
 def test_layout_restatement():
     """compute_alloc_size / get_bl / get_elU (src/init.cpp:4-58, solver.h:4-9, defines.h:12-18)."""
     for n, m in [(4, 3), (6, 3), (10, 7), (30, 9), (4, 7), (64, 16), (5, 1)]:
