@@ -5,7 +5,8 @@
 //   alloc_rows :29-58                         creates the device-resident problem (ms_create)
 //   init_mat :60-98                           device generator (ms_init_formula) for f1 / hilb,
 //                                             otherwise the callback is evaluated into pinned rows
-//   init_mat_file :100-294                    text parser -> pinned staging -> ms_upload_rows
+//   init_mat_file :100-294                    MatrixFileReader (buffered strtod / raw .f64) -> pinned rows
+//                                             -> ms_upload_rows
 //   gather_row / gather_col :309-490          ms_get_row / ms_get_col (one D2H copy)
 //   init_b_get_norm :492-531                  ms_b_and_norm (one pass over the stored triangle)
 //   find_disrep_vec :533-563                  ms_residual
@@ -15,6 +16,7 @@
 #include <cstdarg>
 #include <vector>
 
+#include "ms_matrix_file.h"
 #include "ms_rt.h"
 
 double
@@ -110,31 +112,35 @@ init_mat_file (double **rows_p, size_t n, size_t m, const char *filename)
 {
   (void)m;
   ms_ctx *c = ctx_of (rows_p);
-  FILE *fd = fopen (filename, "r");
-  if (!fd)
+  MatrixFileReader reader;
+  if (!reader.open (filename, n))
     {
       printf ("cant open %s\n", filename);
       return 0;
     }
-  const size_t chunk = std::max<size_t> (1, ((size_t)1 << 21) / n);
-  std::vector<double> rows (chunk * n);
+  // rows are parsed into page-locked memory so that ms_upload_rows can DMA them straight into place
+  const size_t chunk = std::max<size_t> (1, ((size_t)1 << 22) / n);
+  void *pinned = nullptr;
+  std::vector<double> pageable;
+  double *rows;
+  if (ms_host_alloc (&pinned, chunk * n * sizeof (double)) == 0)
+    rows = (double *)pinned;
+  else
+    {
+      pageable.resize (chunk * n);
+      rows = pageable.data ();
+    }
   bool ok = true;
   for (size_t i0 = 0; i0 < n && ok; i0 += chunk)
     {
-      size_t cnt = std::min (chunk, n - i0), got = 0;
-      for (; got < cnt && ok; got++)
-        for (size_t j = 0; j < n; j++)
-          if (fscanf (fd, "%lf", &rows[got * n + j]) != 1)
-            {
-              ok = false;
-              break;
-            }
-      if (!ok)
-        got--;  // the row that hit EOF is incomplete
+      const size_t want = std::min (chunk, n - i0);
+      const size_t got = reader.read_rows (rows, want);
       if (got > 0)
-        must (ms_upload_rows (c, rows.data (), i0, got, n), "ms_upload_rows");
+        must (ms_upload_rows (c, rows, i0, got, n), "ms_upload_rows");
+      ok = got == want;
     }
-  fclose (fd);
+  if (pinned)
+    ms_host_free (pinned);
   if (!ok)
     printf ("unexpected eof of %s\n", filename);
   return ok;

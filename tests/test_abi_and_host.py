@@ -6,6 +6,8 @@ import os
 import re
 import subprocess
 
+import numpy as np
+
 import pytest
 
 import matrix_solver_b200 as ms
@@ -162,3 +164,94 @@ def test_bench_own_arm_refuses_to_run_without_a_gpu():
                          capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert out.returncode != 0
     assert "no CPU fallback" in json.loads(out.stdout.strip().split("\n")[-1])["error"]
+
+
+def _matrix_file_driver(tmp_path):
+    exe = tmp_path / "matrix_file_test"
+    host = os.path.join(ROOT, "matrix_solver_b200", "host")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + host, os.path.join(ROOT, "tests", "matrix_file_test.cpp"),
+                    os.path.join(host, "ms_matrix_file.cpp"), "-o", str(exe)], check=True)
+
+    def run(path, n, mode, chunk=3):
+        out = subprocess.run([str(exe), str(path), str(n), mode, str(chunk)], capture_output=True, text=True,
+                             timeout=120, check=True)
+        return out.stdout
+    return run
+
+
+def test_matrix_file_reader_agrees_with_fscanf(tmp_path):
+    """host/ms_matrix_file.cpp replaces the reference's per-entry fscanf("%lf") (src/init.cpp:100-112)
+    with a buffered strtod parser: same values bit for bit, same acceptance of odd spacing, same
+    verdict on short or malformed files."""
+    import glob
+    run = _matrix_file_driver(tmp_path)
+    # the reference's own fixtures
+    for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "inputs", "*.txt"))):
+        n = len(open(path).readline().split())
+        assert run(path, n, "fast") == run(path, n, "scanf"), path
+        assert run(path, n, "fast", chunk=1000).split("\n")[0] == str(n)
+    rng = np.random.default_rng(3)
+    n = 37
+    a = rng.standard_normal((n, n)) * 10.0 ** rng.integers(-30, 30, (n, n))
+    fmts = ["%.17g", "%.6f", "%e", "%+.3E", "%g"]
+    text = tmp_path / "ragged.txt"
+    with open(text, "w") as f:
+        for i in range(n):
+            for j in range(n):
+                f.write(fmts[(i + j) % len(fmts)] % a[i, j])
+                f.write([" ", "\t", "\n", "   ", " \r\n"][(3 * i + j) % 5])   # line breaks anywhere
+    for chunk in (1, 5, 64):
+        assert run(text, n, "fast", chunk) == run(text, n, "scanf")
+    # values round-trip exactly when written with 17 significant digits
+    exact = tmp_path / "exact.txt"
+    np.savetxt(exact, a, fmt="%.17g")
+    got = run(exact, n, "fast").split()
+    assert int(got[0]) == n
+    assert np.array_equal(np.array([int(h, 16) for h in got[1:]], dtype=np.uint64).view(np.float64).reshape(n, n), a)
+    # short file: the row that hit EOF does not count; garbage stops the parse like "%lf" does
+    body = open(exact).read().split("\n")
+    short = tmp_path / "short.txt"
+    short.write_text("\n".join(body[:20]) + "\n" + " ".join(body[20].split()[:5]))
+    assert run(short, n, "fast") == run(short, n, "scanf")
+    assert run(short, n, "fast").split("\n")[0] == "20"
+    bad = tmp_path / "bad.txt"
+    bad.write_text("\n".join(body[:4]) + "\n1.0 abc 2.0\n" + "\n".join(body[5:]))
+    assert run(bad, n, "fast") == run(bad, n, "scanf")
+    assert run(bad, n, "fast").split("\n")[0] == "4"
+    assert run(tmp_path / "missing.txt", n, "fast") == "cant open\n"
+    # special tokens strtod and "%lf" both take
+    special = tmp_path / "special.txt"
+    special.write_text("inf -inf nan 0x1p-3\n+1.5 1e400 -1e400 1e-400\n4.9e-324 -0x1.8P1 .5 5.\n"
+                       "1E5 -0 2.2250738585072011e-308 0X10\n")
+    assert run(special, 4, "fast") == run(special, 4, "scanf")
+    assert run(special, 4, "fast").split("\n")[0] == "4"
+
+
+def test_matrix_file_reader_tokens_across_buffer_refills(tmp_path):
+    """A file larger than the reader's 8 MB buffer: numbers that straddle a refill boundary must come
+    out whole."""
+    run = _matrix_file_driver(tmp_path)
+    n = 800
+    a = np.random.default_rng(5).standard_normal((n, n))
+    big = tmp_path / "big.txt"
+    np.savetxt(big, a, fmt="%.17g")
+    assert os.path.getsize(big) > 12 << 20
+    got = run(big, n, "fast", chunk=100).split()
+    assert int(got[0]) == n
+    assert np.array_equal(np.array([int(h, 16) for h in got[1:]], dtype=np.uint64).view(np.float64).reshape(n, n), a)
+
+
+def test_matrix_file_reader_raw_f64(tmp_path):
+    """`name.f64`: n*n little-endian doubles, row-major (the large-input format)."""
+    run = _matrix_file_driver(tmp_path)
+    n = 50
+    a = np.random.default_rng(6).standard_normal((n, n))
+    raw = tmp_path / "m.f64"
+    a.astype("<f8").tofile(raw)
+    got = run(raw, n, "fast", chunk=7).split()
+    assert int(got[0]) == n
+    assert np.array_equal(np.array([int(h, 16) for h in got[1:]], dtype=np.uint64).view(np.float64).reshape(n, n), a)
+    a[:33].astype("<f8").tofile(raw)
+    with open(raw, "ab") as f:
+        f.write(b"\0" * 12)
+    assert run(raw, n, "fast", chunk=7).split("\n")[0] == "33"
