@@ -250,8 +250,9 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
       r = ms_p2p_init (c);
       if (r < 0)
         {
-          // peer mapping unavailable (no CUDA IPC between these processes, no peer access ...):
-          // keep going with the NCCL broadcast unless the transport was requested explicitly
+          // ms_p2p_init only fails when a collective inside it failed; a rank that merely cannot map
+          // its peers makes ALL ranks agree on the NCCL broadcast there.  Keep going without the
+          // peer-memory transport unless it was requested explicitly
           const char *force = getenv ("MS_P2P");
           if (force && atoi (force))
             return fail (r);

@@ -84,15 +84,16 @@ ms_p2p_enabled (const ms_ctx *c)
   return c->p2p && st (c)->on;
 }
 
-int
-ms_p2p_init (ms_ctx *c)
+namespace
 {
-  const char *e = getenv ("MS_P2P");
-  if (e && !atoi (e))
-    return MS_OK;  // NCCL broadcast instead
-  p2p_state *p = new p2p_state ();
-  c->p2p = p;
+constexpr int NH = MS_NPB + 2;  // IPC handles per rank: [PB0 PB1 PB2 d sig]
+
+// everything that involves only this rank: flag words, streams, and the handles the peers will open
+int
+local_setup (ms_ctx *c, p2p_state *p, std::vector<char> &mine)
+{
   const int P = c->nranks;
+  const size_t hb = sizeof (cudaIpcMemHandle_t);
   MS_TRY (driver_fn ("cuStreamWaitValue32", (void **)&p->waitValue32));
   MS_TRY (driver_fn ("cuStreamWriteValue32", (void **)&p->writeValue32));
   MS_CUDA (cudaMalloc (&p->sig, SIG_INTS * sizeof (int)));
@@ -105,11 +106,6 @@ ms_p2p_init (ms_ctx *c)
       MS_CUDA (cudaStreamCreateWithFlags (&p->s_peer[r], cudaStreamNonBlocking));
   MS_CUDA (cudaStreamCreateWithFlags (&p->s_misc, cudaStreamNonBlocking));
   MS_CUDA (cudaEventCreateWithFlags (&p->ev_tmp, cudaEventDisableTiming));
-
-  // exchange IPC handles: [PB0 PB1 PB2 d sig] per rank, gathered with the NCCL communicator
-  constexpr int NH = MS_NPB + 2;
-  const size_t hb = sizeof (cudaIpcMemHandle_t);
-  std::vector<char> mine (NH * hb), all ((size_t)P * NH * hb);
   void *ptrs[NH];
   for (int b = 0; b < MS_NPB; b++)
     ptrs[b] = c->PB[b];
@@ -117,18 +113,24 @@ ms_p2p_init (ms_ctx *c)
   ptrs[MS_NPB + 1] = p->sig;
   for (int i = 0; i < NH; i++)
     MS_CUDA (cudaIpcGetMemHandle ((cudaIpcMemHandle_t *)(mine.data () + i * hb), ptrs[i]));
-  char *dbuf = nullptr;
-  MS_CUDA (cudaMalloc (&dbuf, all.size ()));
-  MS_CUDA (cudaMemcpy (dbuf + (size_t)c->rank * NH * hb, mine.data (), mine.size (), cudaMemcpyHostToDevice));
-  MS_TRY (ms_nccl_allgather_bytes (c, dbuf + (size_t)c->rank * NH * hb, dbuf, NH * hb, c->s_main));
-  MS_CUDA (cudaStreamSynchronize (c->s_main));
-  MS_CUDA (cudaMemcpy (all.data (), dbuf, all.size (), cudaMemcpyDeviceToHost));
-  MS_CUDA (cudaFree (dbuf));
+  return MS_OK;
+}
 
+int
+open_peers (ms_ctx *c, p2p_state *p, const std::vector<char> &all)
+{
+  const int P = c->nranks;
+  const size_t hb = sizeof (cudaIpcMemHandle_t);
   for (int b = 0; b < MS_NPB; b++)
     p->peer_pb[b].assign (P, nullptr);
   p->peer_d.assign (P, nullptr);
   p->peer_sig.assign (P, nullptr);
+  const char *force = getenv ("MS_P2P_FORCE_FAIL");  // test hook: pretend rank <value> cannot map its peers
+  if (force && atoi (force) == c->rank)
+    {
+      ms_set_error ("peer mapping failure forced by MS_P2P_FORCE_FAIL");
+      return MS_ERR_CUDA;
+    }
   for (int r = 0; r < P; r++)
     {
       if (r == c->rank)
@@ -140,6 +142,7 @@ ms_p2p_init (ms_ctx *c)
                                                   cudaIpcMemLazyEnablePeerAccess);
           if (err != cudaSuccess)
             {
+              cudaGetLastError ();
               ms_set_error ("cudaIpcOpenMemHandle (rank %d, buffer %d) -> %s", r, i, cudaGetErrorString (err));
               return MS_ERR_CUDA;
             }
@@ -152,9 +155,50 @@ ms_p2p_init (ms_ctx *c)
             p->peer_sig[r] = (int *)q;
         }
     }
-  // nobody may start posting into a peer before that peer has finished this setup
-  MS_TRY (ms_nccl_allreduce_sum (c, c->acc, 1, c->s_main));
+  return MS_OK;
+}
+}  // namespace
+
+// Every rank walks through the same collective calls whatever happens locally, and the ranks then
+// AGREE on the transport: if peer memory cannot be set up anywhere (no P2P between two of the
+// devices, IPC refused in a container ...), everybody uses the ncclBroadcast transport instead.
+int
+ms_p2p_init (ms_ctx *c)
+{
+  const char *e = getenv ("MS_P2P");
+  if (e && !atoi (e))
+    return MS_OK;  // NCCL broadcast instead
+  p2p_state *p = new p2p_state ();
+  c->p2p = p;
+  const int P = c->nranks;
+  const size_t hb = sizeof (cudaIpcMemHandle_t);
+  std::vector<char> mine (NH * hb, 0), all ((size_t)P * NH * hb);
+  int bad = local_setup (c, p, mine) != MS_OK;
+
+  char *dbuf = nullptr;
+  MS_CUDA (cudaMalloc (&dbuf, all.size ()));
+  MS_CUDA (cudaMemcpy (dbuf + (size_t)c->rank * NH * hb, mine.data (), mine.size (), cudaMemcpyHostToDevice));
+  MS_TRY (ms_nccl_allgather_bytes (c, dbuf + (size_t)c->rank * NH * hb, dbuf, NH * hb, c->s_main));
   MS_CUDA (cudaStreamSynchronize (c->s_main));
+  MS_CUDA (cudaMemcpy (all.data (), dbuf, all.size (), cudaMemcpyDeviceToHost));
+  MS_CUDA (cudaFree (dbuf));
+
+  if (!bad)
+    bad = open_peers (c, p, all) != MS_OK;
+  // the agreement doubles as the barrier after which peers may post into this rank's memory
+  int any_bad = bad;
+  MS_TRY (ms_nccl_agree_flag (c, &any_bad));
+  if (any_bad)
+    {
+      if (bad)
+        fprintf (stderr, "matrix_solver_b200: rank %d: %s; all ranks use the ncclBroadcast panel transport\n",
+                 c->rank, ms_last_error ());
+      for (void *q : p->opened)
+        cudaIpcCloseMemHandle (q);
+      p->opened.clear ();
+      p->on = false;
+      return MS_OK;
+    }
   p->on = true;
   return MS_OK;
 }
