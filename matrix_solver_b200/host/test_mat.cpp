@@ -41,7 +41,10 @@ fill_matrix (double **rows_p, const problem_args &a)
 {
   if (a.from_file ())
     return init_mat_file (rows_p, a.n, a.m, a.file);
-  init_mat (rows_p, a.n, a.m, f1);
+  // the reference chooses between its two generators at compile time (test/test_mat.cpp:13-22, :98);
+  // here MS_GENERATOR=hilb selects the second one at run time
+  const char *gen = getenv ("MS_GENERATOR");
+  init_mat (rows_p, a.n, a.m, gen && strcmp (gen, "hilb") == 0 ? hilb : f1);
   return true;
 }
 
