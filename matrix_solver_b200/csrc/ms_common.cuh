@@ -91,6 +91,7 @@ struct ms_ctx
   bool trace = false;       // MS_TRACE=1: timing-enabled step events, read back by ms_debug_trace
   std::vector<float> trace_panel, trace_free, trace_strip;
   bool panel_trsm = true;   // K3 as a triangular solve (default) or as a DMMA product with the inverse
+  int tile_variant = 1;     // 2 = experimental 8-warp tile kernel (MS_TILE_VARIANT / "tile_variant")
 
   double *A = nullptr;       // rows_alloc x ld, row-major; only j >= i meaningful
   double *PB[MS_NPB] = {nullptr, nullptr, nullptr};  // panel buffers, chunk-major [ld/16][hpb][16]

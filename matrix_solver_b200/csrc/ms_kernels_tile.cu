@@ -373,6 +373,386 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+// ============================================================================ DMMA tile kernel, variant 2
+// EXPERIMENTAL — selected with MS_TILE_VARIANT=2 or ms_set_option (ctx, "tile_variant", 2); the default
+// stays variant 1 (above) until this one has been validated and timed on a GPU.
+//
+// Same tiling, operands, fragment mapping, accumulator layout and epilogue as tile_dmma_kernel.  What
+// changes is the register budget.  profiles/r01_kernel_resources.txt: variant 1 has 9 warps, hence 96
+// registers at two CTAs per SM, and its k loop spills (STL/LDL), shuffles accumulators through
+// IMAD.MOVs and loads its fragments with generic LD.E.128 plus 64-bit address arithmetic.  Here:
+//   * 8 warps, 128 registers: no producer warp — thread 0 issues the TMA loads of chunk j + 2 just
+//     before the CTA consumes chunk j (it then only ever waits for a stage that every warp left two
+//     chunks ago);
+//   * shared memory is addressed through the 32-bit shared window, ld.shared.v2.f64 with immediate
+//     offsets: four address registers per lane for the whole k loop;
+//   * the stage index is a compile-time constant of the 4x unrolled k loop (K % 64 == 0 on this
+//     path, so every tile starts at stage 0);
+//   * the fragment loads of k-group G + 1 are issued before the 16 DMMAs of group G by hand (both are
+//     volatile asm, the compiler keeps the order).
+constexpr int TILE2_THREADS = MS_TILE_CONSUMER_WARPS * 32;
+constexpr uint32_t TILE2_AHEAD = MS_STAGES - 2;
+static_assert (MS_STAGES == 4, "variant 2 unrolls the k loop over exactly four stages");
+
+__device__ __forceinline__ double2
+lds_f64x2 (uint32_t addr)
+{
+  double2 v;
+  asm volatile ("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
+struct tile_pos
+{
+  int rt;
+  size_t g_row0, ct;
+};
+
+// tile number t of the launch -> (row tile, its global first row, column tile)
+template <int MODE>
+__device__ __forceinline__ tile_pos
+tile_decode (const tile_args &ta, const int *pref, int n_rt, int t)
+{
+  int lo = 0, hi = n_rt - 1;
+  while (lo < hi)
+    {
+      const int mid = (lo + hi + 1) >> 1;
+      if (pref[mid] <= t)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+  tile_pos tp;
+  tp.rt = lo;
+  tp.g_row0 = tile_row_global (ta, MODE, lo);
+  tp.ct = tile_first_col_tile (ta, MODE, tp.g_row0) + (size_t)(t - pref[lo]);
+  return tp;
+}
+
+// one k chunk (16 k rows) out of stage S_: 4 k-groups x 16 DMMAs
+template <int MODE, int S_>
+__device__ __forceinline__ void
+tile2_consume (double (&acc)[2][2][2][2][2], uint32_t a_e0, uint32_t a_e1, uint32_t b_e0, uint32_t b_e1,
+               const uint32_t *sgn_chunk, bool any_neg)
+{
+  constexpr uint32_t SO = S_ * TILE_STAGE_BYTES;
+  double2 fa[2][2], fb[2][2];  // [buffer][ib or jb]
+#pragma unroll
+  for (int ib = 0; ib < 2; ib++)
+    fa[0][ib] = lds_f64x2 (a_e0 + SO + ib * TILE_CHUNK_BYTES);
+#pragma unroll
+  for (int jb = 0; jb < 2; jb++)
+    fb[0][jb] = lds_f64x2 (b_e0 + SO + jb * TILE_CHUNK_BYTES);
+#pragma unroll
+  for (int G = 0; G < 4; G++)
+    {
+      const int cur = G & 1, nxt = cur ^ 1;
+      if (G < 3)
+        {
+          // group G + 1 = (g2, e2): k rows 8*g2 + 2q + e2 — 1024 bytes per g, the e offset is in a_e1/b_e1
+          const int g2 = (G + 1) >> 1, e2 = (G + 1) & 1;
+          const uint32_t an = (e2 ? a_e1 : a_e0) + SO + g2 * 1024;
+          const uint32_t bn = (e2 ? b_e1 : b_e0) + SO + g2 * 1024;
+#pragma unroll
+          for (int ib = 0; ib < 2; ib++)
+            fa[nxt][ib] = lds_f64x2 (an + ib * TILE_CHUNK_BYTES);
+#pragma unroll
+          for (int jb = 0; jb < 2; jb++)
+            fb[nxt][jb] = lds_f64x2 (bn + jb * TILE_CHUNK_BYTES);
+        }
+      if (MODE == MS_MODE_UPDATE && any_neg)
+        {
+          const uint32_t sm = sgn_chunk[8 * (G >> 1) + (G & 1)];  // k row 8g + 2q + e (2q is in the pointer)
+#pragma unroll
+          for (int ib = 0; ib < 2; ib++)
+            {
+              fa[cur][ib].x = flip_sign (fa[cur][ib].x, sm);
+              fa[cur][ib].y = flip_sign (fa[cur][ib].y, sm);
+            }
+        }
+#pragma unroll
+      for (int ib = 0; ib < 2; ib++)
+#pragma unroll
+        for (int jb = 0; jb < 2; jb++)
+          {
+            dmma_8x8x4 (acc[ib][jb][0][0][0], acc[ib][jb][0][0][1], fa[cur][ib].x, fb[cur][jb].x);
+            dmma_8x8x4 (acc[ib][jb][0][1][0], acc[ib][jb][0][1][1], fa[cur][ib].x, fb[cur][jb].y);
+            dmma_8x8x4 (acc[ib][jb][1][0][0], acc[ib][jb][1][0][1], fa[cur][ib].y, fb[cur][jb].x);
+            dmma_8x8x4 (acc[ib][jb][1][1][0], acc[ib][jb][1][1][1], fa[cur][ib].y, fb[cur][jb].y);
+          }
+    }
+}
+
+// the read-modify-write (UPDATE) / store (PANEL) of one warp's 32 x 32 patch; same ownership map as
+// variant 1: per (ib, jb, a) a lane owns row wm*32 + 16*ib + 2p + a, columns wn*32 + 16*jb + 4q .. +3
+template <int MODE>
+__device__ __forceinline__ void
+tile2_epilogue (const tile_args &ta, const double (&acc)[2][2][2][2][2], double *Ct, int rows_valid, size_t col0,
+                size_t col_lo, int wm, int wn, int p, int q)
+{
+#pragma unroll
+  for (int ib = 0; ib < 2; ib++)
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+      {
+        const int r = wm * 32 + 16 * ib + 2 * p + a;
+        if (r >= rows_valid)
+          continue;
+        double *crow = Ct + (size_t)r * ta.ldc;
+        const size_t cbase = col0 + wn * 32 + 4 * q;
+        double v[2][4];
+#pragma unroll
+        for (int jb = 0; jb < 2; jb++)
+          {
+            v[jb][0] = acc[ib][jb][a][0][0];
+            v[jb][1] = acc[ib][jb][a][1][0];
+            v[jb][2] = acc[ib][jb][a][0][1];
+            v[jb][3] = acc[ib][jb][a][1][1];
+          }
+        const bool fast0 = cbase >= col_lo && cbase + 3 < ta.n;
+        const bool fast1 = cbase + 16 >= col_lo && cbase + 19 < ta.n;
+        if (fast0 && fast1)
+          {
+            double2 *p0 = reinterpret_cast<double2 *> (crow + cbase);
+            double2 *p1 = reinterpret_cast<double2 *> (crow + cbase + 16);
+            if (MODE == MS_MODE_UPDATE)
+              {
+                double2 o00 = p0[0], o01 = p0[1], o10 = p1[0], o11 = p1[1];
+                o00.x -= v[0][0];
+                o00.y -= v[0][1];
+                o01.x -= v[0][2];
+                o01.y -= v[0][3];
+                o10.x -= v[1][0];
+                o10.y -= v[1][1];
+                o11.x -= v[1][2];
+                o11.y -= v[1][3];
+                p0[0] = o00;
+                p0[1] = o01;
+                p1[0] = o10;
+                p1[1] = o11;
+              }
+            else
+              {
+                p0[0] = make_double2 (v[0][0], v[0][1]);
+                p0[1] = make_double2 (v[0][2], v[0][3]);
+                p1[0] = make_double2 (v[1][0], v[1][1]);
+                p1[1] = make_double2 (v[1][2], v[1][3]);
+                double2 *q0 = reinterpret_cast<double2 *> (ta.C2 + chunk_major_index (ta.c2_k0 + r, cbase, ta.c2_H));
+                double2 *q1 = reinterpret_cast<double2 *> (ta.C2 + chunk_major_index (ta.c2_k0 + r, cbase + 16, ta.c2_H));
+                q0[0] = make_double2 (v[0][0], v[0][1]);
+                q0[1] = make_double2 (v[0][2], v[0][3]);
+                q1[0] = make_double2 (v[1][0], v[1][1]);
+                q1[1] = make_double2 (v[1][2], v[1][3]);
+              }
+          }
+        else
+          {
+#pragma unroll
+            for (int jb = 0; jb < 2; jb++)
+#pragma unroll
+              for (int tt = 0; tt < 4; tt++)
+                {
+                  const size_t col = cbase + 16 * jb + tt;
+                  if (col >= col_lo && col < ta.n)
+                    {
+                      if (MODE == MS_MODE_UPDATE)
+                        crow[col] -= v[jb][tt];
+                      else
+                        {
+                          crow[col] = v[jb][tt];
+                          ta.C2[chunk_major_index (ta.c2_k0 + r, col, ta.c2_H)] = v[jb][tt];
+                        }
+                    }
+                }
+          }
+      }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__ (TILE2_THREADS, 2)
+tile_dmma_kernel2 (const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const tile_args ta)
+{
+  extern __shared__ uint8_t smem_raw[];
+  // 1 KB alignment for the 128-byte swizzle, computed as an OFFSET so that `smem` stays a pointer into
+  // the shared window for the compiler (LDS/STS instead of generic accesses)
+  const uint32_t raw_u32 = smem_u32 (smem_raw);
+  const uint32_t pad = ((raw_u32 + 1023u) & ~1023u) - raw_u32;
+  uint8_t *smem = smem_raw + pad;
+  const uint32_t sbase = raw_u32 + pad;
+  uint64_t *full_bar = (uint64_t *)(smem + MS_STAGES * TILE_STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + MS_STAGES;
+  uint32_t *sgn = (uint32_t *)(empty_bar + MS_STAGES + 8);
+  int *pref = (int *)(sgn + TILE_MAX_K);  // pref[rt] = tiles in row tiles < rt
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = ta.K / MS_KC;  // multiple of 4 (the host checks K % 64 == 0)
+  const int n_rt = ta.n_row_tiles;
+
+  if (threadIdx.x == 0)
+    {
+      for (int s = 0; s < MS_STAGES; s++)
+        {
+          mbar_init (&full_bar[s], 1);
+          mbar_init (&empty_bar[s], MS_TILE_CONSUMER_WARPS);
+        }
+      mbar_fence_init ();
+    }
+  int my_neg = 0;
+  for (int k = threadIdx.x; k < ta.K; k += TILE2_THREADS)
+    {
+      const bool neg = ta.dsign != nullptr && ta.dsign[k] < 0.0;
+      sgn[k] = neg ? 0x80000000u : 0u;
+      my_neg |= neg;
+    }
+  for (int rt = threadIdx.x; rt < n_rt; rt += TILE2_THREADS)
+    pref[rt + 1] = tile_count_in_row (ta, MODE, rt);
+  const bool any_neg = __syncthreads_or (my_neg) != 0;
+  if (warp == 0)
+    {
+      // inclusive scan of pref[1..n_rt] by one warp: lane-contiguous segments
+      const int seg = (n_rt + 31) / 32;
+      const int b = lane * seg, e = min (b + seg, n_rt);
+      int sum = 0;
+      for (int i = b; i < e; i++)
+        sum += pref[i + 1];
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+        {
+          int v = __shfl_up_sync (0xffffffffu, incl, o);
+          if (lane >= o)
+            incl += v;
+        }
+      int run = incl - sum;
+      for (int i = b; i < e; i++)
+        {
+          int c = pref[i + 1];
+          pref[i + 1] = run + c;
+          run += c;
+        }
+      if (lane == 0)
+        pref[0] = 0;
+    }
+  __syncthreads ();
+  const int total_tiles = pref[n_rt];
+
+  const int p = lane >> 2, q = lane & 3;
+  const int wm = warp >> 2;  // rows  wm*32
+  const int wn = warp & 3;   // cols  wn*32
+  // fragment addresses inside a stage: k row 8g + 2q + e, 16-byte slot p ^ (2q + e) of the 128-byte row
+  // (the swizzle); g adds 1024 bytes, the second 16-column chunk of the warp adds TILE_CHUNK_BYTES
+  const uint32_t off_e0 = (uint32_t)((2 * q) * 128 + ((p ^ (2 * q)) << 4));
+  const uint32_t off_e1 = (uint32_t)((2 * q + 1) * 128 + ((p ^ (2 * q + 1)) << 4));
+  const uint32_t a_base = sbase + (uint32_t)(wm * 2) * TILE_CHUNK_BYTES;
+  const uint32_t b_base = sbase + TILE_A_BYTES + (uint32_t)(wn * 2) * TILE_CHUNK_BYTES;
+  const uint32_t a_e0 = a_base + off_e0, a_e1 = a_base + off_e1;
+  const uint32_t b_e0 = b_base + off_e0, b_e1 = b_base + off_e1;
+
+  const int t_begin = blockIdx.x * ta.tiles_per_cta;
+  const int t_end = min (total_tiles, t_begin + ta.tiles_per_cta);
+  const uint32_t n_chunks = t_end > t_begin ? (uint32_t)(t_end - t_begin) * (uint32_t)nkb : 0u;
+
+  // producer state, advanced by thread 0 only: next chunk to request and where its operands are
+  uint32_t pj = 0;
+  int p_t = t_begin, p_kb = 0, p_ax = 0, p_ay = 0, p_bc = 0;
+  if (threadIdx.x == 0 && n_chunks > 0)
+    {
+      const tile_pos tp = tile_decode<MODE> (ta, pref, n_rt, p_t);
+      const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(tp.g_row0 / MS_CHUNK) : 0;
+      p_ax = ta.ax0 + achunk0 * ta.axs;
+      p_ay = ta.ay0 + achunk0 * ta.ays;
+      p_bc = (int)(tp.ct * (MS_BN / MS_CHUNK));
+    }
+
+  uint32_t it = 0;  // chunks consumed so far by this CTA (all tiles)
+  for (int t = t_begin; t < t_end; t++)
+    {
+      const tile_pos tp = tile_decode<MODE> (ta, pref, n_rt, t);
+      const size_t g_row0 = tp.g_row0;
+      const size_t col0 = tp.ct * MS_BN;
+      const int rows_valid = g_row0 + MS_BM <= ta.n ? MS_BM : (int)(ta.n - g_row0);
+      const size_t col_lo = (MODE == MS_MODE_UPDATE) ? g_row0 : ta.col_lo_panel;
+      double *Ct = ta.C + (size_t)tp.rt * MS_BM * ta.ldc;
+      if (MODE == MS_MODE_UPDATE)
+        {
+          // the C tile is touched exactly once per launch and comes from HBM: start pulling this
+          // warp's 32 x 32 patch into L2 now so that the epilogue's loads find it there
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            {
+              const int r = wm * 32 + p * 4 + i;
+              const size_t cc = col0 + wn * 32 + q * 8;
+              if (r < rows_valid && cc < ta.n)
+                asm volatile ("prefetch.global.L2 [%0];" ::"l"(Ct + (size_t)r * ta.ldc + cc));
+            }
+        }
+      double acc[2][2][2][2][2];  // [ib][jb][a][b][c0/c1]
+#pragma unroll
+      for (int i = 0; i < 32; i++)
+        (&acc[0][0][0][0][0])[i] = 0.0;
+
+      for (int kb4 = 0; kb4 < nkb; kb4 += MS_STAGES)
+        {
+          const uint32_t ph = (it >> 2) & 1u;  // it % 4 == 0 here: all four stages share the phase
+#pragma unroll
+          for (int s = 0; s < MS_STAGES; s++)
+            {
+              if (threadIdx.x == 0)
+                {
+                  // request chunks up to it + s + TILE2_AHEAD (three at the very start, then one per chunk)
+                  while (pj < n_chunks && pj <= it + (uint32_t)s + TILE2_AHEAD)
+                    {
+                      const uint32_t ps = pj & (MS_STAGES - 1);
+                      mbar_wait (&empty_bar[ps], ((pj >> 2) & 1u) ^ 1u);
+                      mbar_arrive_expect_tx (&full_bar[ps], TILE_STAGE_BYTES);
+                      uint8_t *sa = smem + ps * TILE_STAGE_BYTES;
+                      uint8_t *sb = sa + TILE_A_BYTES;
+                      const int kk = p_kb * MS_KC;
+#pragma unroll
+                      for (int ci = 0; ci < MS_BM / MS_CHUNK; ci++)
+                        tma_load_2d (sa + ci * TILE_CHUNK_BYTES, &tmA, p_ax + ci * ta.axs, p_ay + ci * ta.ays + kk,
+                                     &full_bar[ps]);
+#pragma unroll
+                      for (int cj = 0; cj < MS_BN / MS_CHUNK; cj++)
+                        tma_load_2d (sb + cj * TILE_CHUNK_BYTES, &tmB, ta.bx0 + (p_bc + cj) * ta.bxs,
+                                     ta.by0 + (p_bc + cj) * ta.bys + kk, &full_bar[ps]);
+                      pj++;
+                      if (++p_kb == nkb)
+                        {
+                          p_kb = 0;
+                          if (++p_t < t_end)
+                            {
+                              const tile_pos np = tile_decode<MODE> (ta, pref, n_rt, p_t);
+                              const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(np.g_row0 / MS_CHUNK) : 0;
+                              p_ax = ta.ax0 + achunk0 * ta.axs;
+                              p_ay = ta.ay0 + achunk0 * ta.ays;
+                              p_bc = (int)(np.ct * (MS_BN / MS_CHUNK));
+                            }
+                        }
+                    }
+                }
+              mbar_wait (&full_bar[s], ph);
+              const uint32_t *sgn_chunk = sgn + (kb4 + s) * MS_KC + 2 * q;
+              if (s == 0)
+                tile2_consume<MODE, 0> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
+              else if (s == 1)
+                tile2_consume<MODE, 1> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
+              else if (s == 2)
+                tile2_consume<MODE, 2> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
+              else
+                tile2_consume<MODE, 3> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
+              __syncwarp ();
+              if (lane == 0)
+                mbar_arrive (&empty_bar[s]);
+            }
+          it += MS_STAGES;
+        }
+
+      tile2_epilogue<MODE> (ta, acc, Ct, rows_valid, col0, col_lo, wm, wn, p, q);
+    }
+}
+
 // ---------------------------------------------------------------------------- tensor maps
 typedef CUresult (*encode_fn_t) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -425,6 +805,10 @@ ms_tile_setup (ms_ctx *c)
   MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel<MS_MODE_UPDATE>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
   MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel<MS_MODE_PANEL>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel2<MS_MODE_UPDATE>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel2<MS_MODE_PANEL>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
   c->have_tm = true;
   return MS_OK;
@@ -491,7 +875,10 @@ ms_k_tile_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_en
         continue;
       ta.tiles_per_cta = tiles_per_cta_for (c, total);
       unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
-      tile_dmma_kernel<MS_MODE_UPDATE><<<grid, MS_TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_PB[pb], c->tm_PB[pb], ta);
+      if (c->tile_variant == 2 && K % (MS_KC * MS_STAGES) == 0)
+        tile_dmma_kernel2<MS_MODE_UPDATE><<<grid, TILE2_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_PB[pb], c->tm_PB[pb], ta);
+      else
+        tile_dmma_kernel<MS_MODE_UPDATE><<<grid, MS_TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_PB[pb], c->tm_PB[pb], ta);
       LAUNCH_COUNT (c);
       c->stats.update_launches++;
       c->stats.used_dmma = 1;
@@ -532,7 +919,10 @@ ms_k_tile_panel (ms_ctx *c, int pb, const ms_piece &pc, size_t I, cudaStream_t s
     return MS_OK;
   ta.tiles_per_cta = tiles_per_cta_for (c, total);
   unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
-  tile_dmma_kernel<MS_MODE_PANEL><<<grid, MS_TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, ta);
+  if (c->tile_variant == 2)  // K = 64 here
+    tile_dmma_kernel2<MS_MODE_PANEL><<<grid, TILE2_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, ta);
+  else
+    tile_dmma_kernel<MS_MODE_PANEL><<<grid, MS_TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, ta);
   LAUNCH_COUNT (c);
   MS_CUDA (cudaGetLastError ());
   return MS_OK;

@@ -248,6 +248,38 @@ def test_kernel_families_and_schedules_agree(ms, opts):
         assert np.array_equal(alt["R"], base["R"])           # scheduling must not change arithmetic
 
 
+@pytest.mark.skipif(not os.environ.get("MS_TEST_EXPERIMENTAL"),
+                    reason="experimental tile kernel (variant 2) is opt-in until it has been validated on a GPU: "
+                           "set MS_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("n,m", [(640, 128), (1024, 256), (2048, 64), (1000, 192)])
+def test_experimental_tile_variant2_matches_variant1(ms, n, m):
+    """tile_dmma_kernel2 (8 warps, 128 registers, inline TMA producer) runs the same DMMA sequence per
+    accumulator as the default kernel, so factor and solution must be bit-identical; also with
+    negative d (sign flips) through the dense upload path and with the DMMA panel formulation."""
+    base = gpu_pipeline(ms, n, m)
+    alt = gpu_pipeline(ms, n, m, options=(("tile_variant", 2),))
+    assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
+    base = gpu_pipeline(ms, n, m, options=(("panel_trsm", 0),))
+    alt = gpu_pipeline(ms, n, m, options=(("panel_trsm", 0), ("tile_variant", 2)))
+    assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
+    rng = np.random.default_rng(5)
+    sign = np.where(np.arange(n) % 7 == 3, -1.0, 1.0)
+    L = np.tril(rng.standard_normal((n, n)) * 0.05, -1) + np.eye(n)
+    indef = L @ np.diag(sign * (1 + rng.random(n))) @ L.T
+    out = []
+    for opts in ((), (("tile_variant", 2),)):
+        with ms.Solver(n, m) as s:
+            for k, v in opts:
+                s.set_option(k, v)
+            s.upload_rows(np.ascontiguousarray(indef))
+            norm = s.b_and_norm()
+            fail, _ = s.factor(norm)
+            assert not fail
+            out.append((s.get_upper(), s.get_vec("d")))
+    assert np.array_equal(out[0][1], sign) and np.array_equal(out[1][1], sign)
+    assert np.array_equal(out[0][0], out[1][0])
+
+
 def test_hilbert_generator(ms):
     """The reference's second generator (test/test_mat.cpp:18-22, hilb = 1/(i+j+1)): device generator
     against numpy, and a solve of the (ill-conditioned) system at a size where it is still SPD in fp64."""

@@ -44,6 +44,51 @@ def test_fragment_loads_are_conflict_free_and_fetch_the_intended_elements():
         assert rows == list(range(8 * g, 8 * g + 8))
 
 
+def test_variant2_address_registers_reproduce_the_fragment_offsets():
+    """tile_dmma_kernel2 keeps two per-lane byte offsets (k-set e = 0 / 1) and adds 1024 bytes per k8
+    group as an immediate; that must be the same address variant 1 computes per load."""
+    for lane in range(32):
+        p, q = lane >> 2, lane & 3
+        off_e = [(2 * q + e) * 128 + ((p ^ (2 * q + e)) << 4) for e in range(2)]
+        for g in range(KC // 8):
+            for e in range(2):
+                assert off_e[e] + g * 1024 == fragment_offset(lane, g, e)[1]
+    # the sign word of k-row 8g + 2q + e, read as sgn_chunk[8g + e] with sgn_chunk = sgn + kb*16 + 2q
+    for q in range(4):
+        for G in range(4):
+            g, e = G >> 1, G & 1
+            assert 2 * q + 8 * (G >> 1) + (G & 1) == 8 * g + 2 * q + e
+
+
+def test_variant2_producer_consumer_schedule():
+    """Host-side model of variant 2's single-thread TMA producer: chunk j is requested before chunk
+    j - 2 ... j is consumed (never more than STAGES chunks in flight), every stage is only re-armed after
+    the chunk that used it was consumed by the requesting warp itself, and the parities line up."""
+    STAGES, AHEAD = 4, 2
+    for n_chunks in (4, 8, 16, 64):
+        pj = 0
+        full_phase = [0] * STAGES        # completed phases of full[s]
+        empty_phase = [0] * STAGES       # completed phases of empty[s] (as seen once all 8 warps arrived)
+        in_flight = {}
+        for it in range(n_chunks):
+            while pj < n_chunks and pj <= it + AHEAD:
+                ps = pj % STAGES
+                want = ((pj >> 2) & 1) ^ 1
+                # try_wait.parity(P) succeeds when the phase with parity P has completed, i.e. the
+                # barrier's current phase parity differs from P
+                assert (empty_phase[ps] & 1) != want, ("producer would block on its own warp", it, pj)
+                assert ps not in in_flight
+                in_flight[ps] = pj
+                pj += 1
+            s = it % STAGES
+            assert in_flight.get(s) == it, "consumer waits for a chunk that was never requested"
+            assert (full_phase[s] & 1) == ((it >> 2) & 1)   # waits for the phase with parity (it>>2)&1
+            full_phase[s] += 1                               # ... which the TMA bytes complete
+            del in_flight[s]
+            empty_phase[s] += 1                              # all warps leave the stage
+        assert pj == n_chunks and not in_flight
+
+
 def dmma_8x8x4(c, a, b):
     """mma.sync.aligned.m8n8k4.row.col.f64: lane holds a = A[lane>>2][lane&3], b = B[lane&3][lane>>2],
     c0/c1 = C[lane>>2][(lane&3)*2 + {0,1}]."""
