@@ -487,85 +487,123 @@ tile2_consume (double (&acc)[2][2][2][2][2], uint32_t a_e0, uint32_t a_e1, uint3
 // variant 1: per (ib, jb, a) a lane owns row wm*32 + 16*ib + 2p + a, columns wn*32 + 16*jb + 4q .. +3
 template <int MODE>
 __device__ __forceinline__ void
+tile2_epilogue_row (const tile_args &ta, const double (&acc)[2][2][2][2][2], double *Ct, int ib, int a, int r,
+                    size_t cbase, size_t col_lo)
+{
+  double *crow = Ct + (size_t)r * ta.ldc;
+  double v[2][4];
+#pragma unroll
+  for (int jb = 0; jb < 2; jb++)
+    {
+      v[jb][0] = acc[ib][jb][a][0][0];
+      v[jb][1] = acc[ib][jb][a][1][0];
+      v[jb][2] = acc[ib][jb][a][0][1];
+      v[jb][3] = acc[ib][jb][a][1][1];
+    }
+  const bool fast0 = cbase >= col_lo && cbase + 3 < ta.n;
+  const bool fast1 = cbase + 16 >= col_lo && cbase + 19 < ta.n;
+  if (fast0 && fast1)
+    {
+      double2 *p0 = reinterpret_cast<double2 *> (crow + cbase);
+      double2 *p1 = reinterpret_cast<double2 *> (crow + cbase + 16);
+      if (MODE == MS_MODE_UPDATE)
+        {
+          double2 o00 = p0[0], o01 = p0[1], o10 = p1[0], o11 = p1[1];
+          o00.x -= v[0][0];
+          o00.y -= v[0][1];
+          o01.x -= v[0][2];
+          o01.y -= v[0][3];
+          o10.x -= v[1][0];
+          o10.y -= v[1][1];
+          o11.x -= v[1][2];
+          o11.y -= v[1][3];
+          p0[0] = o00;
+          p0[1] = o01;
+          p1[0] = o10;
+          p1[1] = o11;
+        }
+      else
+        {
+          p0[0] = make_double2 (v[0][0], v[0][1]);
+          p0[1] = make_double2 (v[0][2], v[0][3]);
+          p1[0] = make_double2 (v[1][0], v[1][1]);
+          p1[1] = make_double2 (v[1][2], v[1][3]);
+          double2 *q0 = reinterpret_cast<double2 *> (ta.C2 + chunk_major_index (ta.c2_k0 + r, cbase, ta.c2_H));
+          double2 *q1 = reinterpret_cast<double2 *> (ta.C2 + chunk_major_index (ta.c2_k0 + r, cbase + 16, ta.c2_H));
+          q0[0] = make_double2 (v[0][0], v[0][1]);
+          q0[1] = make_double2 (v[0][2], v[0][3]);
+          q1[0] = make_double2 (v[1][0], v[1][1]);
+          q1[1] = make_double2 (v[1][2], v[1][3]);
+        }
+    }
+  else
+    {
+#pragma unroll
+      for (int jb = 0; jb < 2; jb++)
+#pragma unroll
+        for (int tt = 0; tt < 4; tt++)
+          {
+            const size_t col = cbase + 16 * jb + tt;
+            if (col >= col_lo && col < ta.n)
+              {
+                if (MODE == MS_MODE_UPDATE)
+                  crow[col] -= v[jb][tt];
+                else
+                  {
+                    crow[col] = v[jb][tt];
+                    ta.C2[chunk_major_index (ta.c2_k0 + r, col, ta.c2_H)] = v[jb][tt];
+                  }
+              }
+          }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void
 tile2_epilogue (const tile_args &ta, const double (&acc)[2][2][2][2][2], double *Ct, int rows_valid, size_t col0,
                 size_t col_lo, int wm, int wn, int p, int q)
 {
+  const size_t cbase = col0 + wn * 32 + 4 * q;
+  const bool fast = cbase >= col_lo && cbase + 19 < ta.n;  // both 4-column groups fully inside [col_lo, n)
 #pragma unroll
   for (int ib = 0; ib < 2; ib++)
+    {
+      const int r0 = wm * 32 + 16 * ib + 2 * p;
+      if (MODE == MS_MODE_UPDATE && fast && r0 + 1 < rows_valid)
+        {
+          // interior patch: both rows of the pair in one batch — 8 independent 16-byte loads in flight
+          // before the first subtraction, i.e. two memory round trips per tile instead of four
+          double2 *pa = reinterpret_cast<double2 *> (Ct + (size_t)r0 * ta.ldc + cbase);
+          double2 *pb = reinterpret_cast<double2 *> (Ct + (size_t)(r0 + 1) * ta.ldc + cbase);
+          double2 oa[4] = {pa[0], pa[1], pa[8], pa[9]};  // columns cbase .. +3 and cbase + 16 .. +19
+          double2 ob[4] = {pb[0], pb[1], pb[8], pb[9]};
 #pragma unroll
-    for (int a = 0; a < 2; a++)
-      {
-        const int r = wm * 32 + 16 * ib + 2 * p + a;
-        if (r >= rows_valid)
+          for (int jb = 0; jb < 2; jb++)
+            {
+              oa[2 * jb].x -= acc[ib][jb][0][0][0];
+              oa[2 * jb].y -= acc[ib][jb][0][1][0];
+              oa[2 * jb + 1].x -= acc[ib][jb][0][0][1];
+              oa[2 * jb + 1].y -= acc[ib][jb][0][1][1];
+              ob[2 * jb].x -= acc[ib][jb][1][0][0];
+              ob[2 * jb].y -= acc[ib][jb][1][1][0];
+              ob[2 * jb + 1].x -= acc[ib][jb][1][0][1];
+              ob[2 * jb + 1].y -= acc[ib][jb][1][1][1];
+            }
+          pa[0] = oa[0];
+          pa[1] = oa[1];
+          pa[8] = oa[2];
+          pa[9] = oa[3];
+          pb[0] = ob[0];
+          pb[1] = ob[1];
+          pb[8] = ob[2];
+          pb[9] = ob[3];
           continue;
-        double *crow = Ct + (size_t)r * ta.ldc;
-        const size_t cbase = col0 + wn * 32 + 4 * q;
-        double v[2][4];
+        }
 #pragma unroll
-        for (int jb = 0; jb < 2; jb++)
-          {
-            v[jb][0] = acc[ib][jb][a][0][0];
-            v[jb][1] = acc[ib][jb][a][1][0];
-            v[jb][2] = acc[ib][jb][a][0][1];
-            v[jb][3] = acc[ib][jb][a][1][1];
-          }
-        const bool fast0 = cbase >= col_lo && cbase + 3 < ta.n;
-        const bool fast1 = cbase + 16 >= col_lo && cbase + 19 < ta.n;
-        if (fast0 && fast1)
-          {
-            double2 *p0 = reinterpret_cast<double2 *> (crow + cbase);
-            double2 *p1 = reinterpret_cast<double2 *> (crow + cbase + 16);
-            if (MODE == MS_MODE_UPDATE)
-              {
-                double2 o00 = p0[0], o01 = p0[1], o10 = p1[0], o11 = p1[1];
-                o00.x -= v[0][0];
-                o00.y -= v[0][1];
-                o01.x -= v[0][2];
-                o01.y -= v[0][3];
-                o10.x -= v[1][0];
-                o10.y -= v[1][1];
-                o11.x -= v[1][2];
-                o11.y -= v[1][3];
-                p0[0] = o00;
-                p0[1] = o01;
-                p1[0] = o10;
-                p1[1] = o11;
-              }
-            else
-              {
-                p0[0] = make_double2 (v[0][0], v[0][1]);
-                p0[1] = make_double2 (v[0][2], v[0][3]);
-                p1[0] = make_double2 (v[1][0], v[1][1]);
-                p1[1] = make_double2 (v[1][2], v[1][3]);
-                double2 *q0 = reinterpret_cast<double2 *> (ta.C2 + chunk_major_index (ta.c2_k0 + r, cbase, ta.c2_H));
-                double2 *q1 = reinterpret_cast<double2 *> (ta.C2 + chunk_major_index (ta.c2_k0 + r, cbase + 16, ta.c2_H));
-                q0[0] = make_double2 (v[0][0], v[0][1]);
-                q0[1] = make_double2 (v[0][2], v[0][3]);
-                q1[0] = make_double2 (v[1][0], v[1][1]);
-                q1[1] = make_double2 (v[1][2], v[1][3]);
-              }
-          }
-        else
-          {
-#pragma unroll
-            for (int jb = 0; jb < 2; jb++)
-#pragma unroll
-              for (int tt = 0; tt < 4; tt++)
-                {
-                  const size_t col = cbase + 16 * jb + tt;
-                  if (col >= col_lo && col < ta.n)
-                    {
-                      if (MODE == MS_MODE_UPDATE)
-                        crow[col] -= v[jb][tt];
-                      else
-                        {
-                          crow[col] = v[jb][tt];
-                          ta.C2[chunk_major_index (ta.c2_k0 + r, col, ta.c2_H)] = v[jb][tt];
-                        }
-                    }
-                }
-          }
-      }
+      for (int a = 0; a < 2; a++)
+        if (r0 + a < rows_valid)
+          tile2_epilogue_row<MODE> (ta, acc, Ct, ib, a, r0 + a, cbase, col_lo);
+    }
 }
 
 template <int MODE>
