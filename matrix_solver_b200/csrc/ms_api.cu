@@ -276,6 +276,9 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   e = getenv ("MS_TILE_VARIANT");
   if (e && atoi (e) == 2)
     c->tile_variant = 2;
+  e = getenv ("MS_DIAG_VARIANT");
+  if (e && atoi (e) == 2)
+    c->diag_variant = 2;
   *out = c;
   return MS_OK;
 }
@@ -304,6 +307,11 @@ ms_set_option (ms_ctx *c, const char *key, long value)
     {
       MS_CHECK_ARG (value == 1 || value == 2, "tile_variant is 1 or 2");
       c->tile_variant = (int)value;
+    }
+  else if (!strcmp (key, "diag_variant"))
+    {
+      MS_CHECK_ARG (value == 1 || value == 2, "diag_variant is 1 or 2");
+      c->diag_variant = (int)value;
     }
   else
     {

@@ -92,6 +92,7 @@ struct ms_ctx
   std::vector<float> trace_panel, trace_free, trace_strip;
   bool panel_trsm = true;   // K3 as a triangular solve (default) or as a DMMA product with the inverse
   int tile_variant = 1;     // 2 = experimental 8-warp tile kernel (MS_TILE_VARIANT / "tile_variant")
+  int diag_variant = 1;     // 2 = experimental blocked diag kernel (MS_DIAG_VARIANT / "diag_variant")
 
   double *A = nullptr;       // rows_alloc x ld, row-major; only j >= i meaningful
   double *PB[MS_NPB] = {nullptr, nullptr, nullptr};  // panel buffers, chunk-major [ld/16][hpb][16]

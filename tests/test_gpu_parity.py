@@ -280,6 +280,28 @@ def test_experimental_tile_variant2_matches_variant1(ms, n, m):
     assert np.array_equal(out[0][0], out[1][0])
 
 
+@pytest.mark.skipif(not os.environ.get("MS_TEST_EXPERIMENTAL"),
+                    reason="experimental blocked diag kernel (variant 2) is opt-in until it has been validated on "
+                           "a GPU: set MS_TEST_EXPERIMENTAL=1 (and run the whole suite once with MS_DIAG_VARIANT=2)")
+@pytest.mark.parametrize("n,m", [(64, 64), (200, 64), (640, 128), (1000, 192), (130, 48), (37, 5)])
+def test_experimental_diag_variant2_is_bit_identical(ms, n, m):
+    """diag_kernel_blocked applies the same roundings in the same order as diag_kernel (and the
+    reference): the whole pipeline must not change by a bit, formula and indefinite input alike."""
+    base = gpu_pipeline(ms, n, m)
+    alt = gpu_pipeline(ms, n, m, options=(("diag_variant", 2),))
+    for key in ("R", "d", "y", "x"):
+        assert np.array_equal(alt[key], base[key]), key
+    rng = np.random.default_rng(9)
+    sign = np.where(np.arange(n) % 5 == 2, -1.0, 1.0)
+    L = np.tril(rng.standard_normal((n, n)) * 0.05, -1) + np.eye(n)
+    indef = L @ np.diag(sign * (1 + rng.random(n))) @ L.T
+    base = gpu_pipeline(ms, n, m, dense=indef)
+    alt = gpu_pipeline(ms, n, m, dense=indef, options=(("diag_variant", 2),))
+    assert np.array_equal(base["d"], sign)
+    for key in ("R", "d", "y", "x"):
+        assert np.array_equal(alt[key], base[key]), key
+
+
 def test_hilbert_generator(ms):
     """The reference's second generator (test/test_mat.cpp:18-22, hilb = 1/(i+j+1)): device generator
     against numpy, and a solve of the (ill-conditioned) system at a size where it is still SPD in fp64."""
