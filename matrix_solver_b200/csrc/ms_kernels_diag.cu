@@ -477,7 +477,9 @@ ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_ou
   size_t smem = (((size_t)(want_inverse ? 2 : 1)) * h * (h + 1) + 2 * h) * sizeof (double);
   if (!want_inverse)
     smem = (2 * (size_t)h * (h + 1) + 2 * h) * sizeof (double);  // layout keeps v's slot reserved
-  static bool configured = false;
+  // function attributes are per device: one flag per device index
+  static bool configured_dev[64] = {};
+  bool &configured = configured_dev[c->device & 63];
   if (!configured)
     {
       MS_CUDA (cudaFuncSetAttribute (diag_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -582,7 +584,8 @@ ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t
   MS_CHECK_ARG (h >= 1 && h <= MS_SUB, "trsm panel piece must have 1..64 rows");
   unsigned grid = (unsigned)((n - col_lo + 127) / 128);
   const size_t smem = (size_t)MS_SUB * 128 * sizeof (double);
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  bool &configured = configured_dev[c->device & 63];
   if (!configured)
     {
       MS_CUDA (cudaFuncSetAttribute (trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
