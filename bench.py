@@ -370,7 +370,11 @@ def our_arm(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"formula-generated SPD A_ij=n-max(i,j), n={n}, block m={m}, factor+solve "
                                f"(BASELINE configs[4]); block-row cyclic over {world} GPU(s)",
-                   "n": n, "m": m, "parallelism": f"block-row-cyclic x{world}, NCCL panel broadcast, look-ahead",
+                   "n": n, "m": m,
+                   "parallelism": f"block-row-cyclic x{world}, look-ahead 2, panel over NVLink peer memory "
+                                  f"(copy engines; ncclBroadcast when MS_P2P=0)" if world > 1 else "single GPU, look-ahead 2",
+                   "kernel_variants": {"tile": int(os.environ.get("MS_TILE_VARIANT", "1")),
+                                       "diag": int(os.environ.get("MS_DIAG_VARIANT", "1"))},
                    "l2": "inputs larger than L2 (matrix %.1f GB per GPU)" % (8.0 * n * n / world / 1e9)},
         "factor_ms": factor_ms, "forward_ms": fwd_ms, "backward_ms": bwd_ms, "solve_ms": fwd_ms + bwd_ms,
         "init_ms": init_ms, "bnorm_ms": bnorm_ms,
