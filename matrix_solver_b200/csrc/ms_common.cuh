@@ -113,6 +113,8 @@ struct ms_ctx
 
   CUtensorMap tm_A, tm_PB[MS_NPB], tm_Wt;
   bool have_tm = false;
+  CUtensorMap tm_PB3[MS_NPB];  // rank-3 view {16, hpb, ld/16} of the panel buffers (tile variant 2 only)
+  int tm3_state = 0;           // 0 = not tried yet, 1 = encoded, -1 = unavailable (2-D loads instead)
 
   std::vector<ms_piece> pieces;
   std::vector<size_t> block_first_piece;  // index into pieces, size nblocks+1
@@ -202,6 +204,17 @@ tma_load_2d (void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
   asm volatile ("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
                 " [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32 (dst)),
                 "l"(map), "r"(x), "r"(y), "r"(smem_u32 (bar))
+                : "memory");
+}
+
+// 3-D TMA box load (x fastest): used with the rank-3 view of a chunk-major panel buffer, where one box
+// {16 columns, 16 k rows, 4 chunks} lands as four consecutive 2 KB chunk images.
+__device__ __forceinline__ void
+tma_load_3d (void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+  asm volatile ("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32 (dst)),
+                "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32 (bar))
                 : "memory");
 }
 

@@ -606,10 +606,10 @@ tile2_epilogue (const tile_args &ta, const double (&acc)[2][2][2][2][2], double 
     }
 }
 
-template <int MODE>
+template <int MODE, bool TM3>
 __global__ void __launch_bounds__ (TILE2_THREADS, 2)
 tile_dmma_kernel2 (const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const tile_args ta)
+                   const __grid_constant__ CUtensorMap tm3, const tile_args ta)
 {
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment for the 128-byte swizzle, computed as an OFFSET so that `smem` stays a pointer into
@@ -693,11 +693,12 @@ tile_dmma_kernel2 (const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   // producer state, advanced by thread 0 only: next chunk to request and where its operands are
   uint32_t pj = 0;
-  int p_t = t_begin, p_kb = 0, p_ax = 0, p_ay = 0, p_bc = 0;
+  int p_t = t_begin, p_kb = 0, p_ax = 0, p_ay = 0, p_bc = 0, p_ac = 0;
   if (threadIdx.x == 0 && n_chunks > 0)
     {
       const tile_pos tp = tile_decode<MODE> (ta, pref, n_rt, p_t);
       const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(tp.g_row0 / MS_CHUNK) : 0;
+      p_ac = achunk0;
       p_ax = ta.ax0 + achunk0 * ta.axs;
       p_ay = ta.ay0 + achunk0 * ta.ays;
       p_bc = (int)(tp.ct * (MS_BN / MS_CHUNK));
@@ -747,14 +748,25 @@ tile_dmma_kernel2 (const __grid_constant__ CUtensorMap tmA, const __grid_constan
                       uint8_t *sa = smem + ps * TILE_STAGE_BYTES;
                       uint8_t *sb = sa + TILE_A_BYTES;
                       const int kk = p_kb * MS_KC;
+                      if (MODE == MS_MODE_UPDATE && TM3)
+                        {
+                          // rank-3 view of the chunk-major panel buffer: coordinates (column in chunk, k row,
+                          // chunk); a box holds four chunks, so a stage is three instructions, not twelve
+                          tma_load_3d (sa, &tm3, 0, ta.ay0 + kk, p_ac, &full_bar[ps]);
+                          tma_load_3d (sb, &tm3, 0, ta.by0 + kk, p_bc, &full_bar[ps]);
+                          tma_load_3d (sb + 4 * TILE_CHUNK_BYTES, &tm3, 0, ta.by0 + kk, p_bc + 4, &full_bar[ps]);
+                        }
+                      else
+                        {
 #pragma unroll
-                      for (int ci = 0; ci < MS_BM / MS_CHUNK; ci++)
-                        tma_load_2d (sa + ci * TILE_CHUNK_BYTES, &tmA, p_ax + ci * ta.axs, p_ay + ci * ta.ays + kk,
-                                     &full_bar[ps]);
+                          for (int ci = 0; ci < MS_BM / MS_CHUNK; ci++)
+                            tma_load_2d (sa + ci * TILE_CHUNK_BYTES, &tmA, p_ax + ci * ta.axs,
+                                         p_ay + ci * ta.ays + kk, &full_bar[ps]);
 #pragma unroll
-                      for (int cj = 0; cj < MS_BN / MS_CHUNK; cj++)
-                        tma_load_2d (sb + cj * TILE_CHUNK_BYTES, &tmB, ta.bx0 + (p_bc + cj) * ta.bxs,
-                                     ta.by0 + (p_bc + cj) * ta.bys + kk, &full_bar[ps]);
+                          for (int cj = 0; cj < MS_BN / MS_CHUNK; cj++)
+                            tma_load_2d (sb + cj * TILE_CHUNK_BYTES, &tmB, ta.bx0 + (p_bc + cj) * ta.bxs,
+                                         ta.by0 + (p_bc + cj) * ta.bys + kk, &full_bar[ps]);
+                        }
                       pj++;
                       if (++p_kb == nkb)
                         {
@@ -763,6 +775,7 @@ tile_dmma_kernel2 (const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             {
                               const tile_pos np = tile_decode<MODE> (ta, pref, n_rt, p_t);
                               const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(np.g_row0 / MS_CHUNK) : 0;
+                              p_ac = achunk0;
                               p_ax = ta.ax0 + achunk0 * ta.axs;
                               p_ay = ta.ay0 + achunk0 * ta.ays;
                               p_bc = (int)(np.ct * (MS_BN / MS_CHUNK));
@@ -830,6 +843,49 @@ make_map_2d (CUtensorMap *map, void *base, uint64_t inner, uint64_t rows, uint64
   return MS_OK;
 }
 
+// rank-3 view of a chunk-major panel buffer: (column in chunk, k row, chunk), box = 16 x 16 x 4 chunks
+static int
+make_map_pb3 (CUtensorMap *map, void *base, uint64_t hpb, uint64_t nchunks)
+{
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  MS_CUDA (cudaGetDriverEntryPoint ("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
+    {
+      ms_set_error ("cuTensorMapEncodeTiled not available from the driver");
+      return MS_ERR_CUDA;
+    }
+  cuuint64_t dims[3] = {MS_CHUNK, hpb, nchunks};
+  cuuint64_t strides[2] = {MS_CHUNK * 8, hpb * MS_CHUNK * 8};
+  cuuint32_t box[3] = {MS_CHUNK, MS_KC, 4};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ((encode_fn_t)fn) (map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    {
+      ms_set_error ("cuTensorMapEncodeTiled (rank 3) failed with CUresult %d", (int)r);
+      return MS_ERR_CUDA;
+    }
+  return MS_OK;
+}
+
+// encoded on the first launch of tile variant 2, never on the default path; failure is not an error,
+// the kernel then takes its 2-D loads
+static bool
+tile_tm3_ready (ms_ctx *c)
+{
+  if (c->tm3_state == 0)
+    {
+      const char *e = getenv ("MS_TILE_TMA3");
+      c->tm3_state = (e && !atoi (e)) ? -1 : 1;
+      for (int b = 0; b < MS_NPB && c->tm3_state == 1; b++)
+        if (make_map_pb3 (&c->tm_PB3[b], c->PB[b], c->hpb, c->ld / MS_CHUNK) != MS_OK)
+          c->tm3_state = -1;
+    }
+  return c->tm3_state == 1;
+}
+
 int
 ms_tile_setup (ms_ctx *c)
 {
@@ -844,9 +900,11 @@ ms_tile_setup (ms_ctx *c)
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
   MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel<MS_MODE_PANEL>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
-  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel2<MS_MODE_UPDATE>,
+  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel2<MS_MODE_UPDATE, true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
-  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel2<MS_MODE_PANEL>,
+  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel2<MS_MODE_UPDATE, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel2<MS_MODE_PANEL, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
   c->have_tm = true;
   return MS_OK;
@@ -914,7 +972,14 @@ ms_k_tile_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_en
       ta.tiles_per_cta = tiles_per_cta_for (c, total);
       unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
       if (c->tile_variant == 2 && K % (MS_KC * MS_STAGES) == 0)
-        tile_dmma_kernel2<MS_MODE_UPDATE><<<grid, TILE2_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_PB[pb], c->tm_PB[pb], ta);
+        {
+          if (tile_tm3_ready (c))
+            tile_dmma_kernel2<MS_MODE_UPDATE, true><<<grid, TILE2_THREADS, TILE_SMEM_BYTES, s>>> (
+              c->tm_PB[pb], c->tm_PB[pb], c->tm_PB3[pb], ta);
+          else
+            tile_dmma_kernel2<MS_MODE_UPDATE, false><<<grid, TILE2_THREADS, TILE_SMEM_BYTES, s>>> (
+              c->tm_PB[pb], c->tm_PB[pb], c->tm_PB[pb], ta);
+        }
       else
         tile_dmma_kernel<MS_MODE_UPDATE><<<grid, MS_TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_PB[pb], c->tm_PB[pb], ta);
       LAUNCH_COUNT (c);
@@ -958,7 +1023,7 @@ ms_k_tile_panel (ms_ctx *c, int pb, const ms_piece &pc, size_t I, cudaStream_t s
   ta.tiles_per_cta = tiles_per_cta_for (c, total);
   unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
   if (c->tile_variant == 2)  // K = 64 here
-    tile_dmma_kernel2<MS_MODE_PANEL><<<grid, TILE2_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, ta);
+    tile_dmma_kernel2<MS_MODE_PANEL, false><<<grid, TILE2_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, c->tm_A, ta);
   else
     tile_dmma_kernel<MS_MODE_PANEL><<<grid, MS_TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, ta);
   LAUNCH_COUNT (c);
