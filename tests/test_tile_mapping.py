@@ -170,3 +170,25 @@ def test_chunk_major_panel_buffer_layout():
     # a TMA box (16 columns x 16 k-rows) is one contiguous 2 KB run
     box = sorted(chunk_major_index(k, j, H) for k in range(16, 32) for j in range(48, 64))
     assert box == list(range(box[0], box[0] + 256))
+
+
+def test_rank3_tensor_map_addresses_the_chunk_major_buffer():
+    """Tile variant 2 views a panel buffer through a rank-3 tensor map: dims {16, H, ld/16}, strides
+    {128 B, H*128 B}; coordinate (x, y, z) = (column in chunk, k row, chunk).  That must be the element
+    chunk_major_index(k = y, j = 16 z + x), and a box {16, 16, 4} must land as four consecutive 2 KB
+    chunk images (x fastest, then k, then chunk) — the layout the fragment loads assume."""
+    H, ld = 192, 160
+    for z in range(ld // CHUNK):
+        for y in (0, 1, 17, H - 1):
+            for x in range(CHUNK):
+                byte = x * 8 + y * 128 + z * H * 128
+                assert byte == 8 * chunk_major_index(y, CHUNK * z + x, H)
+    # box at (0, k0, c0): element (x, dy, dz) is written at smem offset ((dz*16 + dy)*16 + x)*8 before
+    # swizzling = chunk image dz (2 KB each), k row dy, column x
+    for dz in range(4):
+        for dy in range(KC):
+            for x in range(CHUNK):
+                linear = ((dz * KC + dy) * CHUNK + x) * 8
+                assert linear == dz * 2048 + dy * 128 + x * 8
+                # the swizzle only permutes 16-byte slots inside a 128-byte row, so the fragment formula holds
+                assert swizzled_byte(dy, x) // 128 == dy
