@@ -705,10 +705,13 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s, cu
   for (size_t pi = c->block_first_piece[I]; pi < c->block_first_piece[I + 1]; pi++)
     {
       const ms_piece &pc = c->pieces[pi];
-      // the block row's pre-update pivot test rides along with its first piece's diag kernel
+      // the block row's pre-update pivot test (src/solver.cpp:117) rides along with its first piece's
+      // diag kernel — except that with look-ahead the later pieces receive their last update (panel
+      // I-1) only at `rest_ready`: their share of the test runs right after that wait, below
       const bool first = pi == c->block_first_piece[I];
+      const bool split_pre = first && rest_ready != nullptr && (size_t)pc.h < rowsI;
       const double *pre = first ? diag0 : nullptr;
-      const int pre_count = first ? (int)rowsI : 0;
+      const int pre_count = first ? (split_pre ? pc.h : (int)rowsI) : 0;
       double *blk = c->A + pc.lrow0 * c->ld + pc.row0;
       double *rows = c->A + pc.lrow0 * c->ld;
       size_t col_lo = pc.row0 + (size_t)pc.h;
@@ -748,7 +751,10 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s, cu
       size_t lr_next = pc.lrow0 + (size_t)pc.h;
       size_t lr_end = lrowI + rowsI;
       if (rest_ready && first && lr_next < lr_end)
-        MS_CUDA (cudaStreamWaitEvent (s, rest_ready, 0));
+        {
+          MS_CUDA (cudaStreamWaitEvent (s, rest_ready, 0));
+          MS_TRY (ms_k_pretest (c, diag0, c->ld, pc.h, (int)rowsI, thresh, s));
+        }
       MS_TRY (do_update (c, pb, I, lr_next, lr_end, pc.h, k0, s, false));
     }
   return MS_OK;

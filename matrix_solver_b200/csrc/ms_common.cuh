@@ -270,6 +270,7 @@ int ms_k_axpy_minus (ms_ctx *c, double *r, const double *b, size_t n, cudaStream
 int ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_out,
                double *wt_out, double *inv_out, const double *pre_diag, size_t pre_ld, int pre_count,
                cudaStream_t s);
+int ms_k_pretest (ms_ctx *c, const double *diag0, size_t ld, int first, int count, double thresh, cudaStream_t s);
 int ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t ld, int h, size_t col_lo,
                      size_t n, const double *dpiece, double *PB, size_t pb_H, size_t pb_k0,
                      cudaStream_t s);

@@ -501,6 +501,29 @@ ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_ou
   return MS_OK;
 }
 
+// The reference's pre-update pivot test (src/solver.cpp:117) for rows [first, count) of a block row
+// whose diagonal starts at diag0: |a_ii| < thresh raises the failure flag.  Used for the pieces after
+// the first one when the look-ahead delivers their last update later than the first piece's (the first
+// piece's share rides along with its diag kernel).
+__global__ void __launch_bounds__ (256)
+pretest_kernel (const double *__restrict__ diag0, size_t ld, int first, int count, double thresh, int *flags)
+{
+  for (int i = first + (int)threadIdx.x; i < count; i += 256)
+    if (fabs (diag0[(size_t)i * ld + i]) < thresh)
+      flags[0] = 1;
+}
+
+int
+ms_k_pretest (ms_ctx *c, const double *diag0, size_t ld, int first, int count, double thresh, cudaStream_t s)
+{
+  if (first >= count)
+    return MS_OK;
+  pretest_kernel<<<1, 256, 0, s>>> (diag0, ld, first, count, thresh, c->flags);
+  LAUNCH_COUNT (c);
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
 // ============================================================================ TRSM panel (K3)
 // X = D * R^{-T} * A for the h rows of one piece and the columns [col_lo, n), in place, plus a copy
 // into the panel buffer.  This is what DRtA / DRtA_l (src/matrix_op.cpp:287-368) compute with the
