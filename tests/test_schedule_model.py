@@ -190,7 +190,7 @@ CASES = [(nb, pieces, P) for nb in (1, 2, 3, 4, 5, 7, 9, 13) for pieces in (1, 2
 
 @pytest.mark.parametrize("nb,pieces,P", CASES)
 def test_factor_schedule_orders_every_conflict(nb, pieces, P):
-    for lookahead in ((True, False) if P == 1 else (True,)):
+    for lookahead in (True, False):
         g, info = build(nb, pieces, P, lookahead)
         reach = g.reach()
         hb = lambda a, b: bool(reach[a] >> b & 1) and a != b
