@@ -192,3 +192,75 @@ def test_rank3_tensor_map_addresses_the_chunk_major_buffer():
                 assert linear == dz * 2048 + dy * 128 + x * 8
                 # the swizzle only permutes 16-byte slots inside a 128-byte row, so the fragment formula holds
                 assert swizzled_byte(dy, x) // 128 == dy
+
+
+# ---- the tile list of one update launch (tile_row_global / tile_first_col_tile / tile_count_in_row and
+# ---- the walk in tile_dmma_kernel: prefix scan over row tiles, binary search, T tiles per CTA)
+def _tile_row_global(lrow_begin, m, rank, nranks, rt):
+    l = lrow_begin + rt * BM
+    lb = l // m
+    return (lb * nranks + rank) * m + (l - lb * m)
+
+
+def _launch_tiles(n, m, rank, nranks, lrow_begin, lrow_end, tiles_per_cta):
+    n_rt = (lrow_end - lrow_begin + BM - 1) // BM
+    total_ct = (n + BN - 1) // BN
+    counts = []
+    for rt in range(n_rt):
+        g = _tile_row_global(lrow_begin, m, rank, nranks, rt)
+        first = g // BN
+        counts.append(max(0, total_ct - first) if g < n else 0)
+    pref = [0]
+    for c in counts:
+        pref.append(pref[-1] + c)
+    total = pref[-1]
+    tiles = []
+    n_cta = (total + tiles_per_cta - 1) // tiles_per_cta
+    for cta in range(n_cta):
+        for t in range(cta * tiles_per_cta, min(total, (cta + 1) * tiles_per_cta)):
+            lo, hi = 0, n_rt - 1
+            while lo < hi:                               # the kernel's binary search
+                mid = (lo + hi + 1) >> 1
+                if pref[mid] <= t:
+                    lo = mid
+                else:
+                    hi = mid - 1
+            g_row0 = _tile_row_global(lrow_begin, m, rank, nranks, lo)
+            ct = g_row0 // BN + (t - pref[lo])
+            tiles.append((lo, g_row0, ct))
+    return tiles, total
+
+
+def test_update_launch_covers_the_stored_trapezoid_exactly_once():
+    """Every stored element (j >= i) of the rows an update launch owns is written by exactly one tile;
+    nothing left of the row's diagonal BLOCK is ever touched; the A operand's first chunk is the panel
+    column that matches the tile's first row."""
+    for n, m, nranks in [(640, 128, 1), (1000, 192, 1), (1024, 256, 2), (1111, 64, 3), (2048, 256, 4), (700, 64, 2)]:
+        nblocks = (n + m - 1) // m
+        for rank in range(nranks):
+            mine = [J for J in range(nblocks) if J % nranks == rank]
+            for I in (0, 1, nblocks // 2):
+                later = [J for J in mine if J > I]
+                if not later:
+                    continue
+                lrow_begin = (later[0] // nranks) * m
+                rows_local = sum(min(m, n - J * m) for J in mine)
+                lrow_end = rows_local
+                for T in (1, 4):
+                    tiles, total = _launch_tiles(n, m, rank, nranks, lrow_begin, lrow_end, T)
+                    assert len(tiles) == total and len(set(tiles)) == total
+                    written = {}
+                    for rt, g_row0, ct in tiles:
+                        assert g_row0 % CHUNK == 0                     # achunk0 = g_row0 / 16 is exact
+                        rows_valid = min(BM, n - g_row0)
+                        for r in range(rows_valid):
+                            i = g_row0 + r
+                            for j in range(max(ct * BN, g_row0), min((ct + 1) * BN, n)):
+                                assert (i, j) not in written
+                                written[(i, j)] = True
+                                assert j >= (i // m) * m               # never left of the diagonal block
+                    want = {(i, j) for J in later for i in range(J * m, min((J + 1) * m, n)) for j in range(i, n)}
+                    assert want <= set(written), (n, m, nranks, rank, I, T)
+                    # what is written beyond the stored triangle is only the lower part of diagonal tiles
+                    for (i, j) in set(written) - want:
+                        assert j < i and j >= (i // BM) * BM
