@@ -257,6 +257,11 @@ ms_p2p_begin_factor (ms_ctx *c)
 //              d_I into its own, then posts credit[rank] = epoch + I + 1 into the owner's memory
 //   owner    : before it writes the same buffer again (panel I+3, factored or pulled) it waits for all
 //              credits of panel I
+// ready[b] is shared by panels I, I+3, I+6 ... which may have different owners, so two GPUs write the
+// same word without a common order; the values only ever grow in program order, and the write for panel
+// I+3 cannot be issued before its owner has consumed panels I+1 and I+2 (whole factorisation steps
+// after the 4-byte copy for panel I was enqueued on an otherwise idle stream).  If that margin ever
+// becomes a concern, index the flags by I % 16 instead of by buffer.
 int
 ms_p2p_send_panel (ms_ctx *c, size_t I, int pb, cudaEvent_t factored)
 {
