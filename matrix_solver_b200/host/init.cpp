@@ -110,8 +110,8 @@ init_mat (double **rows_p, size_t n, size_t m, initializer f)
 bool
 init_mat_file (double **rows_p, size_t n, size_t m, const char *filename)
 {
-  (void)m;
   ms_ctx *c = ctx_of (rows_p);
+  const int rank = ms_rt_init (), size = ms_rt_size ();
   MatrixFileReader reader;
   if (!reader.open (filename, n))
     {
@@ -134,9 +134,19 @@ init_mat_file (double **rows_p, size_t n, size_t m, const char *filename)
   for (size_t i0 = 0; i0 < n && ok; i0 += chunk)
     {
       const size_t want = std::min (chunk, n - i0);
-      const size_t got = reader.read_rows (rows, want);
-      if (got > 0)
-        must (ms_upload_rows (c, rows, i0, got, n), "ms_upload_rows");
+      // a rank only parses (or, for the raw format, only reads) chunks that hold rows it owns
+      bool owned = false;
+      for (size_t I = i0 / m; I * m < i0 + want && !owned; I++)
+        owned = (int)(I % (size_t)size) == rank;
+      size_t got;
+      if (owned)
+        {
+          got = reader.read_rows (rows, want);
+          if (got > 0)
+            must (ms_upload_rows (c, rows, i0, got, n), "ms_upload_rows");
+        }
+      else
+        got = reader.skip_rows (want);
       ok = got == want;
     }
   if (pinned)

@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <sys/types.h>
+
 namespace
 {
 constexpr size_t BUF_BYTES = (size_t)8 << 20;
@@ -116,4 +118,30 @@ MatrixFileReader::read_rows (double *rows, size_t max_rows)
       if (!next_value (&rows[r * n_ + j]))
         return r;
   return max_rows;
+}
+
+size_t
+MatrixFileReader::skip_rows (size_t count)
+{
+  if (!fp_ || count == 0)
+    return 0;
+  if (binary_)
+    {
+      // how many complete rows are left decides the answer; then one seek
+      const off_t here = ftello (fp_);
+      if (here < 0 || fseeko (fp_, 0, SEEK_END) != 0)
+        return 0;
+      const off_t end = ftello (fp_);
+      const size_t row_bytes = n_ * sizeof (double);
+      const size_t left = (size_t)(end - here) / row_bytes;
+      const size_t skipped = count < left ? count : left;
+      fseeko (fp_, here + (off_t)(skipped * row_bytes), SEEK_SET);
+      return skipped;
+    }
+  double ignored;
+  for (size_t r = 0; r < count; r++)
+    for (size_t j = 0; j < n_; j++)
+      if (!next_value (&ignored))
+        return r;
+  return count;
 }

@@ -22,6 +22,9 @@ public:
   // reads up to max_rows complete rows of n doubles into `rows`; returns how many were read.
   // Fewer than asked means the file ended (or held something that is not a number).
   size_t read_rows (double *rows, size_t max_rows);
+  // moves past up to `count` rows without delivering them (a seek for the raw format, a parse for
+  // text); returns how many complete rows were skipped, with the same meaning as read_rows
+  size_t skip_rows (size_t count);
   void close ();
   bool binary () const { return binary_; }
 

@@ -19,6 +19,36 @@ main (int argc, char **argv)
   const char *path = argv[1];
   size_t n = strtoull (argv[2], nullptr, 10);
   bool fast = strcmp (argv[3], "fast") == 0;
+  if (strcmp (argv[3], "alternate") == 0)
+    {
+      // read a chunk, skip a chunk, ... : prints "<first row> <rows>" per delivered chunk, then values
+      size_t chunk = strtoull (argv[4], nullptr, 10);
+      MatrixFileReader r;
+      if (!r.open (path, n))
+        {
+          printf ("cant open\n");
+          return 0;
+        }
+      std::vector<double> buf (chunk * n);
+      bool take = true;
+      for (size_t row = 0; row < n; take = !take)
+        {
+          size_t want = chunk < n - row ? chunk : n - row;
+          size_t got = take ? r.read_rows (buf.data (), want) : r.skip_rows (want);
+          printf ("%s %zu %zu\n", take ? "read" : "skip", row, got);
+          if (take)
+            for (size_t i = 0; i < got * n; i++)
+              {
+                uint64_t u;
+                memcpy (&u, &buf[i], 8);
+                printf ("%016" PRIx64 "\n", u);
+              }
+          row += got;
+          if (got < want)
+            break;
+        }
+      return 0;
+    }
   size_t chunk = strtoull (argv[4], nullptr, 10);
   std::vector<double> a (n * n, 0.0);
   size_t rows = 0;

@@ -255,3 +255,44 @@ def test_matrix_file_reader_raw_f64(tmp_path):
     with open(raw, "ab") as f:
         f.write(b"\0" * 12)
     assert run(raw, n, "fast", chunk=7).split("\n")[0] == "33"
+
+
+def test_matrix_file_reader_skips_rows_of_other_ranks(tmp_path):
+    """init_mat_file lets a rank skip the chunks it owns nothing of: a seek for the raw format, a parse
+    without delivery for text.  Alternating read/skip must deliver exactly the right rows, and a short
+    file must be noticed while skipping too."""
+    run = _matrix_file_driver(tmp_path)
+    n = 23
+    a = np.random.default_rng(8).standard_normal((n, n))
+    text, raw = tmp_path / "m.txt", tmp_path / "m.f64"
+    np.savetxt(text, a, fmt="%.17g")
+    a.astype("<f8").tofile(raw)
+    for path in (text, raw):
+        for chunk in (1, 4, 7):
+            out = run(path, n, "alternate", chunk).split("\n")
+            pos, row, take = 0, 0, True
+            while row < n:
+                want = min(chunk, n - row)
+                kind, first, got = out[pos].split()
+                assert (kind, int(first), int(got)) == ("read" if take else "skip", row, want)
+                pos += 1
+                if take:
+                    vals = np.array([int(h, 16) for h in out[pos:pos + want * n]], dtype=np.uint64).view(np.float64)
+                    assert np.array_equal(vals.reshape(want, n), a[row:row + want])
+                    pos += want * n
+                row += want
+                take = not take
+    # short files: 10 complete rows and a bit
+    np.savetxt(text, a[:10], fmt="%.17g")
+    with open(text, "a") as f:
+        f.write("1.0 2.0\n")
+    a[:10].astype("<f8").tofile(raw)
+    with open(raw, "ab") as f:
+        f.write(b"\0" * 20)
+    for path in (text, raw):
+        out = run(path, n, "alternate", 4).split("\n")
+        heads = [ln for ln in out if ln.startswith(("read", "skip"))]
+        assert heads == ["read 0 4", "skip 4 4", "read 8 2"]
+        out = run(path, n, "alternate", 3).split("\n")
+        heads = [ln for ln in out if ln.startswith(("read", "skip"))]
+        assert heads == ["read 0 3", "skip 3 3", "read 6 3", "skip 9 1"]
