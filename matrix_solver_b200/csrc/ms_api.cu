@@ -273,12 +273,6 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   e = getenv ("MS_NO_LOOKAHEAD");
   if (e && atoi (e))
     c->lookahead = false;
-  e = getenv ("MS_TILE_VARIANT");
-  if (e && atoi (e) == 2)
-    c->tile_variant = 2;
-  e = getenv ("MS_DIAG_VARIANT");
-  if (e && atoi (e) == 2)
-    c->diag_variant = 2;
   *out = c;
   return MS_OK;
 }
@@ -303,16 +297,8 @@ ms_set_option (ms_ctx *c, const char *key, long value)
     c->panel_trsm = value != 0;
   else if (!strcmp (key, "single_launch_sweeps"))
     c->no_sweep = value == 0;
-  else if (!strcmp (key, "tile_variant"))
-    {
-      MS_CHECK_ARG (value == 1 || value == 2, "tile_variant is 1 or 2");
-      c->tile_variant = (int)value;
-    }
-  else if (!strcmp (key, "diag_variant"))
-    {
-      MS_CHECK_ARG (value == 1 || value == 2, "diag_variant is 1 or 2");
-      c->diag_variant = (int)value;
-    }
+  else if (!strcmp (key, "tile_tma3"))
+    c->tm3_state = value ? 0 : -1;  // 0 = encode the rank-3 maps on the next update launch
   else
     {
       ms_set_error ("unknown option %s", key);

@@ -57,7 +57,6 @@ constexpr int MS_KC = 16;     // k rows per pipeline stage
 constexpr int MS_STAGES = 4;  // TMA ring depth
 constexpr int MS_NPB = 3;     // panel buffers in rotation (look-ahead depth 2)
 constexpr int MS_TILE_CONSUMER_WARPS = 8;
-constexpr int MS_TILE_THREADS = (MS_TILE_CONSUMER_WARPS + 1) * 32;
 
 static inline size_t
 round_up (size_t v, size_t a)
@@ -91,8 +90,6 @@ struct ms_ctx
   bool trace = false;       // MS_TRACE=1: timing-enabled step events, read back by ms_debug_trace
   std::vector<float> trace_panel, trace_free, trace_strip;
   bool panel_trsm = true;   // K3 as a triangular solve (default) or as a DMMA product with the inverse
-  int tile_variant = 1;     // 2 = experimental 8-warp tile kernel (MS_TILE_VARIANT / "tile_variant")
-  int diag_variant = 1;     // 2 = experimental blocked diag kernel (MS_DIAG_VARIANT / "diag_variant")
 
   double *A = nullptr;       // rows_alloc x ld, row-major; only j >= i meaningful
   double *PB[MS_NPB] = {nullptr, nullptr, nullptr};  // panel buffers, chunk-major [ld/16][hpb][16]
@@ -113,8 +110,8 @@ struct ms_ctx
 
   CUtensorMap tm_A, tm_PB[MS_NPB], tm_Wt;
   bool have_tm = false;
-  CUtensorMap tm_PB3[MS_NPB];  // rank-3 view {16, hpb, ld/16} of the panel buffers (tile variant 2 only)
-  int tm3_state = 0;           // 0 = not tried yet, 1 = encoded, -1 = unavailable (2-D loads instead)
+  CUtensorMap tm_PB3[MS_NPB];  // rank-3 view {16, hpb, ld/16} of the panel buffers (update launches)
+  int tm3_state = 0;           // 0 = not tried yet, 1 = encoded, -1 = unavailable or MS_TILE_TMA3=0 (2-D loads instead)
 
   std::vector<ms_piece> pieces;
   std::vector<size_t> block_first_piece;  // index into pieces, size nblocks+1

@@ -241,230 +241,6 @@ diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *
 #endif
 }
 
-// ---------------------------------------------------------------------------- K1, blocked schedule
-// EXPERIMENTAL — MS_DIAG_VARIANT=2 / ms_set_option (ctx, "diag_variant", 2); off by default and not yet
-// run on a GPU.  h <= 64.
-//
-// diag_kernel above pays one __syncthreads and one shared-memory round trip per pivot (measured ~870
-// cycles per pivot, 34-40 us per 64-row piece: the longest link of the panel chain).  Here the pivots go
-// in strips of 8:
-//   warp 0     : holds the strip (8 rows, lane = columns lane and lane + 32) in registers, first applies
-//                the previous strip's pivots to it, then factors it with shuffles only — no barrier, no
-//                shared-memory traffic on the sqrt / divide chain;
-//   warps 1-7  : meanwhile apply the PREVIOUS strip's 8 pivots to all rows below the current strip;
-//   one __syncthreads per strip.
-// Every entry still receives its subtractions in ascending pivot order, each product and difference
-// rounded separately, so the result is the reference's bit for bit (CPU model of this schedule against
-// the oracle: tests/test_diag_schedule.py).
-__global__ void __launch_bounds__ (256)
-diag_kernel_blocked (double *__restrict__ blk, size_t ld, int h, double thresh, double *__restrict__ d_out,
-                     double *__restrict__ wt_out, int wt_h, double *__restrict__ inv_out, int want_inverse,
-                     const double *__restrict__ pre_diag, size_t pre_ld, int pre_count, int *flags)
-{
-  constexpr int NB = 8;
-  extern __shared__ double smd[];
-  const int S = h + 1;
-  double *a = smd;
-  double *v = a + (size_t)h * S;
-  double *rdiag = v + (size_t)h * S;
-  double *dd = rdiag + h;
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  const int lane = tid & 31, warp = tid >> 5;
-
-  // the reference's pre-update pivot test (src/solver.cpp:117) for the whole block row
-  for (int i = tid; i < pre_count; i += 256)
-    if (fabs (pre_diag[(size_t)i * pre_ld + i]) < thresh)
-      flags[0] = 1;
-
-  for (int i = ty; i < h; i += 16)
-    for (int j = tx; j < h; j += 16)
-      {
-        a[i * S + j] = j >= i ? blk[(size_t)i * ld + j] : 0.0;
-        if (want_inverse)
-          v[i * S + j] = 0.0;
-      }
-  __syncthreads ();
-
-  const int nblk = (h + NB - 1) / NB;
-  for (int b = 0; b < nblk; b++)
-    {
-      const int i0 = NB * b;
-      if (warp == 0)
-        {
-          const int j0 = lane, j1 = lane + 32;
-          double c[NB][2];
-#pragma unroll
-          for (int u = 0; u < NB; u++)
-            {
-              const int row = i0 + u;
-              c[u][0] = (row < h && j0 < h && j0 >= row) ? a[row * S + j0] : 0.0;
-              c[u][1] = (row < h && j1 < h && j1 >= row) ? a[row * S + j1] : 0.0;
-            }
-          if (b > 0)
-            {
-              // the previous strip's pivots (rows i0-8 .. i0-1, final in shared memory), ascending
-#pragma unroll
-              for (int t = 0; t < NB; t++)
-                {
-                  const int i = i0 - NB + t;
-                  const double di = dd[i];
-                  const double rj0 = j0 < h ? a[i * S + j0] : 0.0;
-                  const double rj1 = j1 < h ? a[i * S + j1] : 0.0;
-#pragma unroll
-                  for (int u = 0; u < NB; u++)
-                    {
-                      const int k = i0 + u;
-                      const double rk = k < h ? a[i * S + k] : 0.0;
-                      c[u][0] = __dsub_rn (c[u][0], __dmul_rn (__dmul_rn (rk, rj0), di));
-                      c[u][1] = __dsub_rn (c[u][1], __dmul_rn (__dmul_rn (rk, rj1), di));
-                    }
-                }
-            }
-          // factor the strip out of registers
-#pragma unroll
-          for (int t = 0; t < NB; t++)
-            {
-              const int row = i0 + t;
-              if (row < h)
-                {
-                  const double s = __shfl_sync (0xffffffffu, (row & 32) ? c[t][1] : c[t][0], row & 31);
-                  const double di = s > 0 ? 1.0 : -1.0;
-                  const double rii = __dsqrt_rn (fabs (s));
-                  const double den = __dmul_rn (rii, di);
-                  if (lane == (row & 31))
-                    {
-                      rdiag[row] = rii;
-                      dd[row] = di;
-                      if (fabs (rii) < thresh)
-                        flags[0] = 1;
-                    }
-                  if (j0 > row && j0 < h)
-                    c[t][0] = __ddiv_rn (c[t][0], den);
-                  if (j1 > row && j1 < h)
-                    c[t][1] = __ddiv_rn (c[t][1], den);
-#pragma unroll
-                  for (int u = t + 1; u < NB; u++)
-                    {
-                      const int k = i0 + u;  // r(row, k) lives in the lane that owns column k
-                      const double rk = __shfl_sync (0xffffffffu, (k & 32) ? c[t][1] : c[t][0], k & 31);
-                      c[u][0] = __dsub_rn (c[u][0], __dmul_rn (__dmul_rn (rk, c[t][0]), di));
-                      c[u][1] = __dsub_rn (c[u][1], __dmul_rn (__dmul_rn (rk, c[t][1]), di));
-                    }
-                }
-            }
-#pragma unroll
-          for (int u = 0; u < NB; u++)
-            {
-              const int row = i0 + u;
-              if (row < h)
-                {
-                  if (j0 > row && j0 < h)
-                    a[row * S + j0] = c[u][0];
-                  if (j1 > row && j1 < h)
-                    a[row * S + j1] = c[u][1];
-                }
-            }
-        }
-      else if (b > 0 && i0 + NB < h)
-        {
-          // warps 1-7 (14 x 16 threads): the previous strip's pivots into rows k >= i0 + 8, columns j >= k.
-          // i0 + 8 >= 16, so at most 48 rows and columns remain: 4 x 14 rows, 3 x 16 columns per thread.
-          constexpr int NTR = 4, NTC = 3;
-          const int base = i0 + NB;
-          const int t2 = tid - 32, ux = t2 & 15, uy = t2 >> 4;
-          double c[NTR][NTC];
-#pragma unroll
-          for (int u = 0; u < NTR; u++)
-#pragma unroll
-            for (int w = 0; w < NTC; w++)
-              {
-                const int k = base + uy + 14 * u, j = base + ux + 16 * w;
-                c[u][w] = (k < h && j < h && j >= k) ? a[k * S + j] : 0.0;
-              }
-#pragma unroll
-          for (int t = 0; t < NB; t++)
-            {
-              const int i = i0 - NB + t;
-              const double di = dd[i];
-              double rk[NTR], rj[NTC];
-#pragma unroll
-              for (int u = 0; u < NTR; u++)
-                {
-                  const int k = base + uy + 14 * u;
-                  rk[u] = k < h ? a[i * S + k] : 0.0;
-                }
-#pragma unroll
-              for (int w = 0; w < NTC; w++)
-                {
-                  const int j = base + ux + 16 * w;
-                  rj[w] = j < h ? a[i * S + j] : 0.0;
-                }
-#pragma unroll
-              for (int u = 0; u < NTR; u++)
-#pragma unroll
-                for (int w = 0; w < NTC; w++)
-                  c[u][w] = __dsub_rn (c[u][w], __dmul_rn (__dmul_rn (rk[u], rj[w]), di));
-            }
-#pragma unroll
-          for (int u = 0; u < NTR; u++)
-#pragma unroll
-            for (int w = 0; w < NTC; w++)
-              {
-                const int k = base + uy + 14 * u, j = base + ux + 16 * w;
-                if (k < h && j < h && j >= k)
-                  a[k * S + j] = c[u][w];
-              }
-        }
-      __syncthreads ();
-    }
-
-  // ---- K2: inverse, one thread per column, rows bottom-up, k ascending (as in diag_kernel)
-  if (want_inverse)
-    {
-      for (int j = tid; j < h; j += 256)
-        {
-          for (int i = j; i >= 0; i--)
-            {
-              double val;
-              if (i == j)
-                val = __ddiv_rn (1.0, rdiag[i]);
-              else
-                {
-                  double sum = 0;
-                  for (int k = i + 1; k <= j; k++)
-                    sum = __dadd_rn (sum, __dmul_rn (a[i * S + k], v[k * S + j]));
-                  val = __ddiv_rn (-sum, rdiag[i]);
-                }
-              v[i * S + j] = val;
-            }
-        }
-      __syncthreads ();
-    }
-
-  // ---- write back: R in place (upper), d, the inverse, and Wt = inverse * D (chunk-major)
-  for (int i = ty; i < h; i += 16)
-    for (int j = tx; j < h; j += 16)
-      {
-        if (j > i)
-          blk[(size_t)i * ld + j] = a[i * S + j];
-        else if (j == i)
-          blk[(size_t)i * ld + j] = rdiag[i];
-        if (inv_out)
-          inv_out[(size_t)i * h + j] = j >= i ? v[i * S + j] : 0.0;
-      }
-  if (d_out)
-    for (int i = tid; i < h; i += 256)
-      d_out[i] = dd[i];
-  if (wt_out)
-    for (int k = ty; k < wt_h; k += 16)
-      for (int i = tx; i < wt_h; i += 16)
-        {
-          double val = (k < h && i < h && i >= k) ? v[k * S + i] * dd[i] : 0.0;
-          wt_out[chunk_major_index (k, i, wt_h)] = val;
-        }
-}
-
 // d_out: h doubles (device), wt_out: chunk-major [MS_SUB/16][MS_SUB][16] or null.  The inverse is
 // computed only when someone consumes it (wt_out / inv_out).  pre_diag/pre_ld/pre_count: diagonal to
 // run the pre-update pivot test on (the whole block row, handed to its first piece).
@@ -484,13 +260,9 @@ ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_ou
     {
       MS_CUDA (cudaFuncSetAttribute (diag_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       MS_CUDA (cudaFuncSetAttribute (diag_kernel<8, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      MS_CUDA (cudaFuncSetAttribute (diag_kernel_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       configured = true;
     }
-  if (h <= 64 && c->diag_variant == 2)
-    diag_kernel_blocked<<<1, 256, smem, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse,
-                                             pre_diag, pre_ld, pre_count, c->flags);
-  else if (h <= 64)
+  if (h <= 64)
     diag_kernel<5, 4><<<1, 256, smem, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse,
                                            pre_diag, pre_ld, pre_count, c->flags);
   else

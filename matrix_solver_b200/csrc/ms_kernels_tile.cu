@@ -5,9 +5,9 @@
 // in two flavours:
 //   * tile_dmma_kernel  — the hot path.  64 x 128 output tile per CTA, fp64 tensor cores
 //     (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), operands streamed by TMA
-//     (cp.async.bulk.tensor.2d, 128-byte swizzle) through a 4-stage mbarrier ring by one
-//     producer warp, 8 consumer warps (32 x 32 each, 32 fp64 accumulators per lane), two
-//     CTAs per SM so one CTA's read-modify-write epilogue overlaps the other's math.
+//     (cp.async.bulk.tensor, 128-byte swizzle) through a 4-stage mbarrier ring, 8 warps
+//     (32 x 32 each, 32 fp64 accumulators per lane), two CTAs per SM so one CTA's
+//     read-modify-write epilogue overlaps the other's math.
 //   * gemm_generic_kernel — bounds-checked CUDA-core (DFMA) kernel for block sizes the tile
 //     kernel does not take (m % 64 != 0).  Same contract, still on the device.
 //
@@ -96,303 +96,30 @@ tile_count_in_row (const tile_args &ta, int mode, int rt)
 }
 
 // Each CTA walks `tiles_per_cta` consecutive entries of the list of stored tiles (same row tile =
-// same A operand for neighbours).  The TMA ring keeps running across those tiles, so the producer is
-// already fetching the next tile's operands while the consumers run the current tile's epilogue.
-// CTAs are deliberately NOT persistent for the whole launch: retiring every few tiles lets the
-// hardware scheduler hand SM slots to the high-priority panel stream (look-ahead) and keeps the two
-// CTAs that share an SM out of phase, so one CTA's epilogue overlaps the other's DMMA loop.
-template <int MODE>
-__global__ void __launch_bounds__ (MS_TILE_THREADS, 2)
-tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const tile_args ta)
-{
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t *full_bar = (uint64_t *)(smem + MS_STAGES * TILE_STAGE_BYTES);
-  uint64_t *empty_bar = full_bar + MS_STAGES;
-  uint32_t *sgn = (uint32_t *)(empty_bar + MS_STAGES + 8);
-  int *pref = (int *)(sgn + TILE_MAX_K);  // pref[rt] = tiles in row tiles < rt
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = ta.K / MS_KC;
-  const int n_rt = ta.n_row_tiles;
-
-  if (threadIdx.x == 0)
-    {
-      for (int s = 0; s < MS_STAGES; s++)
-        {
-          mbar_init (&full_bar[s], 1);
-          mbar_init (&empty_bar[s], MS_TILE_CONSUMER_WARPS);
-        }
-      mbar_fence_init ();
-    }
-  int my_neg = 0;
-  for (int k = threadIdx.x; k < ta.K; k += MS_TILE_THREADS)
-    {
-      const bool neg = ta.dsign != nullptr && ta.dsign[k] < 0.0;
-      sgn[k] = neg ? 0x80000000u : 0u;
-      my_neg |= neg;
-    }
-  for (int rt = threadIdx.x; rt < n_rt; rt += MS_TILE_THREADS)
-    pref[rt + 1] = tile_count_in_row (ta, MODE, rt);
-  const bool any_neg = __syncthreads_or (my_neg) != 0;
-  if (warp == 0)
-    {
-      // exclusive scan of pref[1..n_rt] by one warp: lane-contiguous segments
-      const int seg = (n_rt + 31) / 32;
-      const int b = lane * seg, e = min (b + seg, n_rt);
-      int sum = 0;
-      for (int i = b; i < e; i++)
-        sum += pref[i + 1];
-      int incl = sum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
-        {
-          int v = __shfl_up_sync (0xffffffffu, incl, o);
-          if (lane >= o)
-            incl += v;
-        }
-      int run = incl - sum;
-      for (int i = b; i < e; i++)
-        {
-          int c = pref[i + 1];
-          pref[i + 1] = run + c;  // inclusive
-          run += c;
-        }
-      if (lane == 0)
-        pref[0] = 0;
-    }
-  __syncthreads ();
-  const int total_tiles = pref[n_rt];
-
-  const int p = lane >> 2, q = lane & 3;
-  const int wm = warp >> 2;  // consumer rows  wm*32
-  const int wn = warp & 3;   // consumer cols  wn*32
-  uint32_t it = 0;           // running k-stage counter (same sequence in producer and consumers)
-
-  const int t_begin = blockIdx.x * ta.tiles_per_cta;
-  const int t_end = min (total_tiles, t_begin + ta.tiles_per_cta);
-  for (int t = t_begin; t < t_end; t++)
-    {
-      int lo = 0, hi = n_rt - 1;
-      while (lo < hi)
-        {
-          const int mid = (lo + hi + 1) >> 1;
-          if (pref[mid] <= t)
-            lo = mid;
-          else
-            hi = mid - 1;
-        }
-      const int rt = lo;
-      const size_t g_row0 = tile_row_global (ta, MODE, rt);
-      const size_t ct = tile_first_col_tile (ta, MODE, g_row0) + (size_t)(t - pref[rt]);
-      const size_t col0 = ct * MS_BN;
-
-      if (warp == MS_TILE_CONSUMER_WARPS)
-        {
-          // ---------------------------------------------------------------- TMA producer
-          if (lane == 0)
-            {
-              // A chunk 0 = the 16 panel columns that match the tile's first output row
-              const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(g_row0 / MS_CHUNK) : 0;
-              const int ax = ta.ax0 + achunk0 * ta.axs, ay = ta.ay0 + achunk0 * ta.ays;
-              const int bchunk0 = (int)(ct * (MS_BN / MS_CHUNK));
-              for (int kb = 0; kb < nkb; kb++, it++)
-                {
-                  const int s = it % MS_STAGES;
-                  const uint32_t ph = (it / MS_STAGES) & 1u;
-                  mbar_wait (&empty_bar[s], ph ^ 1u);
-                  mbar_arrive_expect_tx (&full_bar[s], TILE_STAGE_BYTES);
-                  uint8_t *sa = smem + s * TILE_STAGE_BYTES;
-                  uint8_t *sb = sa + TILE_A_BYTES;
-                  const int kk = kb * MS_KC;
-#pragma unroll
-                  for (int ci = 0; ci < MS_BM / MS_CHUNK; ci++)
-                    tma_load_2d (sa + ci * TILE_CHUNK_BYTES, &tmA, ax + ci * ta.axs, ay + ci * ta.ays + kk,
-                                 &full_bar[s]);
-#pragma unroll
-                  for (int cj = 0; cj < MS_BN / MS_CHUNK; cj++)
-                    tma_load_2d (sb + cj * TILE_CHUNK_BYTES, &tmB, ta.bx0 + (bchunk0 + cj) * ta.bxs,
-                                 ta.by0 + (bchunk0 + cj) * ta.bys + kk, &full_bar[s]);
-                }
-            }
-          continue;
-        }
-
-      // -------------------------------------------------------------------- DMMA consumers
-      const int rows_valid = g_row0 + MS_BM <= ta.n ? MS_BM : (int)(ta.n - g_row0);
-      const size_t col_lo = (MODE == MS_MODE_UPDATE) ? g_row0 : ta.col_lo_panel;
-      double *Ct = ta.C + (size_t)rt * MS_BM * ta.ldc;
-      if (MODE == MS_MODE_UPDATE)
-        {
-          // the C tile is touched exactly once per launch and comes from HBM: start pulling this
-          // warp's 32 x 32 patch into L2 now so that the epilogue's loads find it there
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-            {
-              const int r = wm * 32 + p * 4 + i;       // 8 lanes groups x 4 rows = 32 rows
-              const size_t cc = col0 + wn * 32 + q * 8; // 4 x 64 B = the patch's 256 B row segment
-              if (r < rows_valid && cc < ta.n)
-                asm volatile ("prefetch.global.L2 [%0];" ::"l"(Ct + (size_t)r * ta.ldc + cc));
-            }
-        }
-      double acc[2][2][2][2][2];  // [ib][jb][a][b][e]
-#pragma unroll
-      for (int i = 0; i < 32; i++)
-        (&acc[0][0][0][0][0])[i] = 0.0;
-
-      for (int kb = 0; kb < nkb; kb++, it++)
-        {
-          const int s = it % MS_STAGES;
-          const uint32_t ph = (it / MS_STAGES) & 1u;
-          mbar_wait (&full_bar[s], ph);
-          const uint8_t *sa = smem + s * TILE_STAGE_BYTES + (wm * 2) * TILE_CHUNK_BYTES;
-          const uint8_t *sb = smem + s * TILE_STAGE_BYTES + TILE_A_BYTES + (wn * 2) * TILE_CHUNK_BYTES;
-#pragma unroll
-          for (int g = 0; g < MS_KC / 8; g++)
-            {
-#pragma unroll
-              for (int e = 0; e < 2; e++)
-                {
-                  const int kr = 8 * g + 2 * q + e;                    // k row inside the stage
-                  const int off = kr * 128 + ((p ^ (kr & 7)) << 4);    // swizzled 16-byte slot
-                  double2 fa[2], fb[2];
-#pragma unroll
-                  for (int ib = 0; ib < 2; ib++)
-                    fa[ib] = *reinterpret_cast<const double2 *> (sa + ib * TILE_CHUNK_BYTES + off);
-#pragma unroll
-                  for (int jb = 0; jb < 2; jb++)
-                    fb[jb] = *reinterpret_cast<const double2 *> (sb + jb * TILE_CHUNK_BYTES + off);
-                  if (MODE == MS_MODE_UPDATE && any_neg)
-                    {
-                      const uint32_t sm = sgn[kb * MS_KC + kr];
-#pragma unroll
-                      for (int ib = 0; ib < 2; ib++)
-                        {
-                          fa[ib].x = flip_sign (fa[ib].x, sm);
-                          fa[ib].y = flip_sign (fa[ib].y, sm);
-                        }
-                    }
-#pragma unroll
-                  for (int ib = 0; ib < 2; ib++)
-#pragma unroll
-                    for (int jb = 0; jb < 2; jb++)
-                      {
-                        dmma_8x8x4 (acc[ib][jb][0][0][0], acc[ib][jb][0][0][1], fa[ib].x, fb[jb].x);
-                        dmma_8x8x4 (acc[ib][jb][0][1][0], acc[ib][jb][0][1][1], fa[ib].x, fb[jb].y);
-                        dmma_8x8x4 (acc[ib][jb][1][0][0], acc[ib][jb][1][0][1], fa[ib].y, fb[jb].x);
-                        dmma_8x8x4 (acc[ib][jb][1][1][0], acc[ib][jb][1][1][1], fa[ib].y, fb[jb].y);
-                      }
-                }
-            }
-          __syncwarp ();
-          if (lane == 0)
-            mbar_arrive (&empty_bar[s]);
-        }
-
-      // -------------------------------------------------------------------- epilogue
-      // lane owns, per (ib, jb, a): row wm*32 + 16*ib + 2p + a, columns wn*32 + 16*jb + 4q .. +3.
-      // One row (= 4 x 16-byte vectors) is loaded as a batch before it is used, so a warp pays one
-      // memory round trip per row instead of one per vector.
-#pragma unroll
-      for (int ib = 0; ib < 2; ib++)
-#pragma unroll
-        for (int a = 0; a < 2; a++)
-          {
-            const int r = wm * 32 + 16 * ib + 2 * p + a;
-            if (r >= rows_valid)
-              continue;
-            double *crow = Ct + (size_t)r * ta.ldc;
-            const size_t cbase = col0 + wn * 32 + 4 * q;
-            double v[2][4];
-#pragma unroll
-            for (int jb = 0; jb < 2; jb++)
-              {
-                v[jb][0] = acc[ib][jb][a][0][0];
-                v[jb][1] = acc[ib][jb][a][1][0];
-                v[jb][2] = acc[ib][jb][a][0][1];
-                v[jb][3] = acc[ib][jb][a][1][1];
-              }
-            const bool fast0 = cbase >= col_lo && cbase + 3 < ta.n;
-            const bool fast1 = cbase + 16 >= col_lo && cbase + 19 < ta.n;
-            if (fast0 && fast1)
-              {
-                double2 *p0 = reinterpret_cast<double2 *> (crow + cbase);
-                double2 *p1 = reinterpret_cast<double2 *> (crow + cbase + 16);
-                if (MODE == MS_MODE_UPDATE)
-                  {
-                    double2 o00 = p0[0], o01 = p0[1], o10 = p1[0], o11 = p1[1];
-                    o00.x -= v[0][0];
-                    o00.y -= v[0][1];
-                    o01.x -= v[0][2];
-                    o01.y -= v[0][3];
-                    o10.x -= v[1][0];
-                    o10.y -= v[1][1];
-                    o11.x -= v[1][2];
-                    o11.y -= v[1][3];
-                    p0[0] = o00;
-                    p0[1] = o01;
-                    p1[0] = o10;
-                    p1[1] = o11;
-                  }
-                else
-                  {
-                    p0[0] = make_double2 (v[0][0], v[0][1]);
-                    p0[1] = make_double2 (v[0][2], v[0][3]);
-                    p1[0] = make_double2 (v[1][0], v[1][1]);
-                    p1[1] = make_double2 (v[1][2], v[1][3]);
-                    double2 *q0 = reinterpret_cast<double2 *> (ta.C2 + chunk_major_index (ta.c2_k0 + r, cbase, ta.c2_H));
-                    double2 *q1 = reinterpret_cast<double2 *> (ta.C2 + chunk_major_index (ta.c2_k0 + r, cbase + 16, ta.c2_H));
-                    q0[0] = make_double2 (v[0][0], v[0][1]);
-                    q0[1] = make_double2 (v[0][2], v[0][3]);
-                    q1[0] = make_double2 (v[1][0], v[1][1]);
-                    q1[1] = make_double2 (v[1][2], v[1][3]);
-                  }
-              }
-            else
-              {
-#pragma unroll
-                for (int jb = 0; jb < 2; jb++)
-#pragma unroll
-                  for (int tt = 0; tt < 4; tt++)
-                    {
-                      const size_t col = cbase + 16 * jb + tt;
-                      if (col >= col_lo && col < ta.n)
-                        {
-                          if (MODE == MS_MODE_UPDATE)
-                            crow[col] -= v[jb][tt];
-                          else
-                            {
-                              crow[col] = v[jb][tt];
-                              ta.C2[chunk_major_index (ta.c2_k0 + r, col, ta.c2_H)] = v[jb][tt];
-                            }
-                        }
-                    }
-              }
-          }
-    }
-}
-
-// ============================================================================ DMMA tile kernel, variant 2
-// EXPERIMENTAL — selected with MS_TILE_VARIANT=2 or ms_set_option (ctx, "tile_variant", 2); the default
-// stays variant 1 (above) until this one has been validated and timed on a GPU.
+// same A operand for neighbours).  The TMA ring keeps running across those tiles, so the next tile's
+// operands are already in flight during the epilogue.  CTAs are deliberately NOT persistent for the
+// whole launch: retiring every few tiles lets the hardware scheduler hand SM slots to the
+// high-priority panel stream (look-ahead) and keeps the two CTAs that share an SM out of phase, so one
+// CTA's epilogue overlaps the other's DMMA loop.
 //
-// Same tiling, operands, fragment mapping, accumulator layout and epilogue as tile_dmma_kernel.  What
-// changes is the register budget.  profiles/r01_kernel_resources.txt: variant 1 has 9 warps, hence 96
-// registers at two CTAs per SM, and its k loop spills (STL/LDL), shuffles accumulators through
-// IMAD.MOVs and loads its fragments with generic LD.E.128 plus 64-bit address arithmetic.  Here:
-//   * 8 warps, 128 registers: no producer warp — thread 0 issues the TMA loads of chunk j + 2 just
-//     before the CTA consumes chunk j (it then only ever waits for a stage that every warp left two
-//     chunks ago);
+// Register budget and instruction mix (round 2: this kernel replaced the 9-warp producer/consumer
+// variant of round 1 after an A/B on the GPU, profiles/r02_experimental_ab.txt: 2807 vs 3005 ms at
+// n = 65536):
+//   * 8 warps, 128 registers, two CTAs per SM: no producer warp — thread 0 issues the TMA loads of
+//     chunk j + 2 just before the CTA consumes chunk j (it then only ever waits for a stage that every
+//     warp left two chunks ago);
+//   * UPDATE mode loads through a rank-3 tensor map over the chunk-major panel buffer ({16, hpb,
+//     ld/16}, box {16, 16, 4 chunks}): three TMA instructions per stage instead of twelve — this is
+//     where the 7 % came from (the 2-D loads, MS_TILE_TMA3=0, measure 3007 ms);
 //   * shared memory is addressed through the 32-bit shared window, ld.shared.v2.f64 with immediate
 //     offsets: four address registers per lane for the whole k loop;
 //   * the stage index is a compile-time constant of the 4x unrolled k loop (K % 64 == 0 on this
 //     path, so every tile starts at stage 0);
 //   * the fragment loads of k-group G + 1 are issued before the 16 DMMAs of group G by hand (both are
 //     volatile asm, the compiler keeps the order).
-constexpr int TILE2_THREADS = MS_TILE_CONSUMER_WARPS * 32;
-constexpr uint32_t TILE2_AHEAD = MS_STAGES - 2;
-static_assert (MS_STAGES == 4, "variant 2 unrolls the k loop over exactly four stages");
+constexpr int TILE_THREADS = MS_TILE_CONSUMER_WARPS * 32;
+constexpr uint32_t TILE_AHEAD = MS_STAGES - 2;
+static_assert (MS_STAGES == 4, "the k loop is unrolled over exactly four stages");
 
 __device__ __forceinline__ double2
 lds_f64x2 (uint32_t addr)
@@ -432,7 +159,7 @@ tile_decode (const tile_args &ta, const int *pref, int n_rt, int t)
 // one k chunk (16 k rows) out of stage S_: 4 k-groups x 16 DMMAs
 template <int MODE, int S_>
 __device__ __forceinline__ void
-tile2_consume (double (&acc)[2][2][2][2][2], uint32_t a_e0, uint32_t a_e1, uint32_t b_e0, uint32_t b_e1,
+tile_consume (double (&acc)[2][2][2][2][2], uint32_t a_e0, uint32_t a_e1, uint32_t b_e0, uint32_t b_e1,
                const uint32_t *sgn_chunk, bool any_neg)
 {
   constexpr uint32_t SO = S_ * TILE_STAGE_BYTES;
@@ -484,10 +211,10 @@ tile2_consume (double (&acc)[2][2][2][2][2], uint32_t a_e0, uint32_t a_e1, uint3
 }
 
 // the read-modify-write (UPDATE) / store (PANEL) of one warp's 32 x 32 patch; same ownership map as
-// variant 1: per (ib, jb, a) a lane owns row wm*32 + 16*ib + 2p + a, columns wn*32 + 16*jb + 4q .. +3
+// per (ib, jb, a) a lane owns row wm*32 + 16*ib + 2p + a, columns wn*32 + 16*jb + 4q .. +3
 template <int MODE>
 __device__ __forceinline__ void
-tile2_epilogue_row (const tile_args &ta, const double (&acc)[2][2][2][2][2], double *Ct, int ib, int a, int r,
+tile_epilogue_row (const tile_args &ta, const double (&acc)[2][2][2][2][2], double *Ct, int ib, int a, int r,
                     size_t cbase, size_t col_lo)
 {
   double *crow = Ct + (size_t)r * ta.ldc;
@@ -560,7 +287,7 @@ tile2_epilogue_row (const tile_args &ta, const double (&acc)[2][2][2][2][2], dou
 
 template <int MODE>
 __device__ __forceinline__ void
-tile2_epilogue (const tile_args &ta, const double (&acc)[2][2][2][2][2], double *Ct, int rows_valid, size_t col0,
+tile_epilogue (const tile_args &ta, const double (&acc)[2][2][2][2][2], double *Ct, int rows_valid, size_t col0,
                 size_t col_lo, int wm, int wn, int p, int q)
 {
   const size_t cbase = col0 + wn * 32 + 4 * q;
@@ -602,13 +329,13 @@ tile2_epilogue (const tile_args &ta, const double (&acc)[2][2][2][2][2], double 
 #pragma unroll
       for (int a = 0; a < 2; a++)
         if (r0 + a < rows_valid)
-          tile2_epilogue_row<MODE> (ta, acc, Ct, ib, a, r0 + a, cbase, col_lo);
+          tile_epilogue_row<MODE> (ta, acc, Ct, ib, a, r0 + a, cbase, col_lo);
     }
 }
 
 template <int MODE, bool TM3>
-__global__ void __launch_bounds__ (TILE2_THREADS, 2)
-tile_dmma_kernel2 (const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__ (TILE_THREADS, 2)
+tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tm3, const tile_args ta)
 {
   extern __shared__ uint8_t smem_raw[];
@@ -637,13 +364,13 @@ tile_dmma_kernel2 (const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_fence_init ();
     }
   int my_neg = 0;
-  for (int k = threadIdx.x; k < ta.K; k += TILE2_THREADS)
+  for (int k = threadIdx.x; k < ta.K; k += TILE_THREADS)
     {
       const bool neg = ta.dsign != nullptr && ta.dsign[k] < 0.0;
       sgn[k] = neg ? 0x80000000u : 0u;
       my_neg |= neg;
     }
-  for (int rt = threadIdx.x; rt < n_rt; rt += TILE2_THREADS)
+  for (int rt = threadIdx.x; rt < n_rt; rt += TILE_THREADS)
     pref[rt + 1] = tile_count_in_row (ta, MODE, rt);
   const bool any_neg = __syncthreads_or (my_neg) != 0;
   if (warp == 0)
@@ -739,8 +466,8 @@ tile_dmma_kernel2 (const __grid_constant__ CUtensorMap tmA, const __grid_constan
             {
               if (threadIdx.x == 0)
                 {
-                  // request chunks up to it + s + TILE2_AHEAD (three at the very start, then one per chunk)
-                  while (pj < n_chunks && pj <= it + (uint32_t)s + TILE2_AHEAD)
+                  // request chunks up to it + s + TILE_AHEAD (three at the very start, then one per chunk)
+                  while (pj < n_chunks && pj <= it + (uint32_t)s + TILE_AHEAD)
                     {
                       const uint32_t ps = pj & (MS_STAGES - 1);
                       mbar_wait (&empty_bar[ps], ((pj >> 2) & 1u) ^ 1u);
@@ -786,13 +513,13 @@ tile_dmma_kernel2 (const __grid_constant__ CUtensorMap tmA, const __grid_constan
               mbar_wait (&full_bar[s], ph);
               const uint32_t *sgn_chunk = sgn + (kb4 + s) * MS_KC + 2 * q;
               if (s == 0)
-                tile2_consume<MODE, 0> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
+                tile_consume<MODE, 0> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
               else if (s == 1)
-                tile2_consume<MODE, 1> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
+                tile_consume<MODE, 1> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
               else if (s == 2)
-                tile2_consume<MODE, 2> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
+                tile_consume<MODE, 2> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
               else
-                tile2_consume<MODE, 3> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
+                tile_consume<MODE, 3> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
               __syncwarp ();
               if (lane == 0)
                 mbar_arrive (&empty_bar[s]);
@@ -800,7 +527,7 @@ tile_dmma_kernel2 (const __grid_constant__ CUtensorMap tmA, const __grid_constan
           it += MS_STAGES;
         }
 
-      tile2_epilogue<MODE> (ta, acc, Ct, rows_valid, col0, col_lo, wm, wn, p, q);
+      tile_epilogue<MODE> (ta, acc, Ct, rows_valid, col0, col_lo, wm, wn, p, q);
     }
 }
 
@@ -870,7 +597,7 @@ make_map_pb3 (CUtensorMap *map, void *base, uint64_t hpb, uint64_t nchunks)
   return MS_OK;
 }
 
-// encoded on the first launch of tile variant 2, never on the default path; failure is not an error,
+// encoded on the first update launch; failure is not an error,
 // the kernel then takes its 2-D loads
 static bool
 tile_tm3_ready (ms_ctx *c)
@@ -896,15 +623,11 @@ ms_tile_setup (ms_ctx *c)
   for (int b = 0; b < MS_NPB; b++)
     MS_TRY (make_map_2d (&c->tm_PB[b], c->PB[b], MS_CHUNK, (c->ld / MS_CHUNK) * c->hpb, MS_CHUNK * 8));
   MS_TRY (make_map_2d (&c->tm_Wt, c->Wt, MS_CHUNK, (MS_SUB / MS_CHUNK) * MS_SUB, MS_CHUNK * 8));
-  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel<MS_MODE_UPDATE>,
+  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel<MS_MODE_UPDATE, true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
-  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel<MS_MODE_PANEL>,
+  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel<MS_MODE_UPDATE, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
-  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel2<MS_MODE_UPDATE, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
-  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel2<MS_MODE_UPDATE, false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
-  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel2<MS_MODE_PANEL, false>,
+  MS_CUDA (cudaFuncSetAttribute (tile_dmma_kernel<MS_MODE_PANEL, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
   c->have_tm = true;
   return MS_OK;
@@ -947,7 +670,7 @@ ms_k_tile_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_en
   if (lrow_end <= lrow_begin)
     return MS_OK;
   MS_CHECK_ARG (c->have_tm, "tile kernel not set up");
-  MS_CHECK_ARG (K % MS_KC == 0 && K <= TILE_MAX_K, "K must be a multiple of 16 and <= 1024");
+  MS_CHECK_ARG (K % (MS_KC * MS_STAGES) == 0 && K <= TILE_MAX_K, "K must be a multiple of 64 and <= 1024");
   MS_CHECK_ARG (lrow_begin % MS_BM == 0, "row range must start on a tile boundary");
   for (size_t lr = lrow_begin; lr < lrow_end; lr += (size_t)TILE_MAX_RT * MS_BM)
     {
@@ -971,17 +694,12 @@ ms_k_tile_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_en
         continue;
       ta.tiles_per_cta = tiles_per_cta_for (c, total);
       unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
-      if (c->tile_variant == 2 && K % (MS_KC * MS_STAGES) == 0)
-        {
-          if (tile_tm3_ready (c))
-            tile_dmma_kernel2<MS_MODE_UPDATE, true><<<grid, TILE2_THREADS, TILE_SMEM_BYTES, s>>> (
-              c->tm_PB[pb], c->tm_PB[pb], c->tm_PB3[pb], ta);
-          else
-            tile_dmma_kernel2<MS_MODE_UPDATE, false><<<grid, TILE2_THREADS, TILE_SMEM_BYTES, s>>> (
-              c->tm_PB[pb], c->tm_PB[pb], c->tm_PB[pb], ta);
-        }
+      if (tile_tm3_ready (c))
+        tile_dmma_kernel<MS_MODE_UPDATE, true><<<grid, TILE_THREADS, TILE_SMEM_BYTES, s>>> (
+          c->tm_PB[pb], c->tm_PB[pb], c->tm_PB3[pb], ta);
       else
-        tile_dmma_kernel<MS_MODE_UPDATE><<<grid, MS_TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_PB[pb], c->tm_PB[pb], ta);
+        tile_dmma_kernel<MS_MODE_UPDATE, false><<<grid, TILE_THREADS, TILE_SMEM_BYTES, s>>> (
+          c->tm_PB[pb], c->tm_PB[pb], c->tm_PB[pb], ta);
       LAUNCH_COUNT (c);
       c->stats.update_launches++;
       c->stats.used_dmma = 1;
@@ -1022,10 +740,7 @@ ms_k_tile_panel (ms_ctx *c, int pb, const ms_piece &pc, size_t I, cudaStream_t s
     return MS_OK;
   ta.tiles_per_cta = tiles_per_cta_for (c, total);
   unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
-  if (c->tile_variant == 2)  // K = 64 here
-    tile_dmma_kernel2<MS_MODE_PANEL, false><<<grid, TILE2_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, c->tm_A, ta);
-  else
-    tile_dmma_kernel<MS_MODE_PANEL><<<grid, MS_TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, ta);
+  tile_dmma_kernel<MS_MODE_PANEL, false><<<grid, TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, c->tm_A, ta);
   LAUNCH_COUNT (c);
   MS_CUDA (cudaGetLastError ());
   return MS_OK;

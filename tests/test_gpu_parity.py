@@ -248,26 +248,21 @@ def test_kernel_families_and_schedules_agree(ms, opts):
         assert np.array_equal(alt["R"], base["R"])           # scheduling must not change arithmetic
 
 
-@pytest.mark.skipif(not os.environ.get("MS_TEST_EXPERIMENTAL"),
-                    reason="experimental tile kernel (variant 2) is opt-in until it has been validated on a GPU: "
-                           "set MS_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("n,m", [(640, 128), (1024, 256), (2048, 64), (1000, 192)])
-def test_experimental_tile_variant2_matches_variant1(ms, n, m):
-    """tile_dmma_kernel2 (8 warps, 128 registers, inline TMA producer) runs the same DMMA sequence per
-    accumulator as the default kernel, so factor and solution must be bit-identical; also with
-    negative d (sign flips) through the dense upload path and with the DMMA panel formulation."""
+def test_tile_kernel_rank3_and_2d_tma_loads_agree(ms, n, m):
+    """The update launches feed the tile kernel through a rank-3 tensor map over the chunk-major panel
+    buffer (three TMA instructions per stage); "tile_tma3" = 0 selects the twelve 2-D loads that land
+    the same shared-memory image.  Same DMMA sequence per accumulator, so factor and solution must be
+    bit-identical — also with negative d (sign flips) through the dense upload path."""
     base = gpu_pipeline(ms, n, m)
-    alt = gpu_pipeline(ms, n, m, options=(("tile_variant", 2),))
-    assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
-    base = gpu_pipeline(ms, n, m, options=(("panel_trsm", 0),))
-    alt = gpu_pipeline(ms, n, m, options=(("panel_trsm", 0), ("tile_variant", 2)))
+    alt = gpu_pipeline(ms, n, m, options=(("tile_tma3", 0),))
     assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
     rng = np.random.default_rng(5)
     sign = np.where(np.arange(n) % 7 == 3, -1.0, 1.0)
     L = np.tril(rng.standard_normal((n, n)) * 0.05, -1) + np.eye(n)
     indef = L @ np.diag(sign * (1 + rng.random(n))) @ L.T
     out = []
-    for opts in ((), (("tile_variant", 2),)):
+    for opts in ((), (("tile_tma3", 0),)):
         with ms.Solver(n, m) as s:
             for k, v in opts:
                 s.set_option(k, v)
@@ -278,28 +273,6 @@ def test_experimental_tile_variant2_matches_variant1(ms, n, m):
             out.append((s.get_upper(), s.get_vec("d")))
     assert np.array_equal(out[0][1], sign) and np.array_equal(out[1][1], sign)
     assert np.array_equal(out[0][0], out[1][0])
-
-
-@pytest.mark.skipif(not os.environ.get("MS_TEST_EXPERIMENTAL"),
-                    reason="experimental blocked diag kernel (variant 2) is opt-in until it has been validated on "
-                           "a GPU: set MS_TEST_EXPERIMENTAL=1 (and run the whole suite once with MS_DIAG_VARIANT=2)")
-@pytest.mark.parametrize("n,m", [(64, 64), (200, 64), (640, 128), (1000, 192), (130, 48), (37, 5)])
-def test_experimental_diag_variant2_is_bit_identical(ms, n, m):
-    """diag_kernel_blocked applies the same roundings in the same order as diag_kernel (and the
-    reference): the whole pipeline must not change by a bit, formula and indefinite input alike."""
-    base = gpu_pipeline(ms, n, m)
-    alt = gpu_pipeline(ms, n, m, options=(("diag_variant", 2),))
-    for key in ("R", "d", "y", "x"):
-        assert np.array_equal(alt[key], base[key]), key
-    rng = np.random.default_rng(9)
-    sign = np.where(np.arange(n) % 5 == 2, -1.0, 1.0)
-    L = np.tril(rng.standard_normal((n, n)) * 0.05, -1) + np.eye(n)
-    indef = L @ np.diag(sign * (1 + rng.random(n))) @ L.T
-    base = gpu_pipeline(ms, n, m, dense=indef)
-    alt = gpu_pipeline(ms, n, m, dense=indef, options=(("diag_variant", 2),))
-    assert np.array_equal(base["d"], sign)
-    for key in ("R", "d", "y", "x"):
-        assert np.array_equal(alt[key], base[key]), key
 
 
 def test_hilbert_generator(ms):

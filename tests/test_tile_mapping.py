@@ -44,9 +44,9 @@ def test_fragment_loads_are_conflict_free_and_fetch_the_intended_elements():
         assert rows == list(range(8 * g, 8 * g + 8))
 
 
-def test_variant2_address_registers_reproduce_the_fragment_offsets():
-    """tile_dmma_kernel2 keeps two per-lane byte offsets (k-set e = 0 / 1) and adds 1024 bytes per k8
-    group as an immediate; that must be the same address variant 1 computes per load."""
+def test_address_registers_reproduce_the_fragment_offsets():
+    """tile_dmma_kernel keeps two per-lane byte offsets (k-set e = 0 / 1) and adds 1024 bytes per k8
+    group as an immediate; that must be the address of the fragment map above."""
     for lane in range(32):
         p, q = lane >> 2, lane & 3
         off_e = [(2 * q + e) * 128 + ((p ^ (2 * q + e)) << 4) for e in range(2)]
@@ -60,8 +60,8 @@ def test_variant2_address_registers_reproduce_the_fragment_offsets():
             assert 2 * q + 8 * (G >> 1) + (G & 1) == 8 * g + 2 * q + e
 
 
-def test_variant2_producer_consumer_schedule():
-    """Host-side model of variant 2's single-thread TMA producer: chunk j is requested before chunk
+def test_producer_consumer_schedule():
+    """Host-side model of the tile kernel's single-thread TMA producer: chunk j is requested before chunk
     j - 2 ... j is consumed (never more than STAGES chunks in flight), every stage is only re-armed after
     the chunk that used it was consumed by the requesting warp itself, and the parities line up."""
     STAGES, AHEAD = 4, 2
@@ -173,7 +173,7 @@ def test_chunk_major_panel_buffer_layout():
 
 
 def test_rank3_tensor_map_addresses_the_chunk_major_buffer():
-    """Tile variant 2 views a panel buffer through a rank-3 tensor map: dims {16, H, ld/16}, strides
+    """The tile kernel views a panel buffer through a rank-3 tensor map: dims {16, H, ld/16}, strides
     {128 B, H*128 B}; coordinate (x, y, z) = (column in chunk, k row, chunk).  That must be the element
     chunk_major_index(k = y, j = 16 z + x), and a box {16, 16, 4} must land as four consecutive 2 KB
     chunk images (x fastest, then k, then chunk) — the layout the fragment loads assume."""
