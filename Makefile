@@ -33,7 +33,7 @@ cli: $(BINDIR)/test_mat
 $(BINDIR)/test_mat: lib $(wildcard $(HOST)/*.cpp) $(wildcard $(HOST)/*.h)
 	@mkdir -p $(BINDIR)
 	$(CXX) -std=c++17 -O2 -Wall -Wextra -I$(HOST) -Iinclude -o $@ $(wildcard $(HOST)/*.cpp) \
-	    -L$(LIBDIR) -lms_b200 -Wl,-rpath,'$$ORIGIN/../lib' -ldl
+	    -L$(LIBDIR) -lms_b200 -Wl,-rpath,'$$ORIGIN/../lib' -ldl -pthread
 
 oracle:
 	$(MAKE) -C oracle oracle

@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """bench.py — factor GFLOP/s (n^3/3) + solve time of the blocked R^T D R path on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 65536] [--m 256]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config c2|c3|c4|c5] [--n N --m M]
+
+--config picks one of BASELINE.json's formula configurations: c2 = n 4096 / m 64, c3 = 16384 / 128,
+c4 = 32768 / 256, c5 = 65536 / 256 (default: the configuration the headline metric is quoted on).
 
 N > 1 is launched by torchrun (one rank per GPU; RANK / LOCAL_RANK / WORLD_SIZE from the env).
 Prints ONE JSON line on rank 0.
@@ -16,12 +20,18 @@ HBM: device generator -> b and ||A||_inf -> factor -> forward sweep -> backward 
   e2e          = (n^3/3) / (host-buffer time-to-solution): the step's matrix comes from page-locked
                  HOST memory through ms_upload_rows, then b/norm, factor, both sweeps and the D2H
                  read of x and d — all inside the timed region
-  roofline     = the trailing-update tile kernel (K4+K5): algorithmic flops of its launches /
-                 their summed CUDA-event durations, against the fp64 tensor-pipe peak measured in
-                 this run (register-only DMMA.8x8x4 issue loop)
-  cpu_baseline = the UNMODIFIED reference (oracle/_ref/test_mat_ref, its own `elapsed` timer) on
-                 the box's host cores through the minimpi shim, on a bounded sample of the same
-                 workload (smaller n, same generator and m)
+  roofline     = the trailing-update tile kernel (K4+K5): algorithmic flops of its launches / the
+                 device time in which at least one of them was running (union of the per-launch
+                 CUDA-event intervals, so never more than factor_ms), against the fp64 tensor-pipe
+                 peak measured in this run (register-only DMMA.8x8x4 issue loop; a cuBLAS Dgemm
+                 8192^3 figure is printed beside it as a library yardstick)
+  parity       = checked OUTSIDE the timed region on the last factorisation, at every N: ||A||_inf ==
+                 n(n+1)/2, d == 1, >= 64 rows of R (block-row / rank boundaries, last block row)
+                 against the analytic factor R_ij = (n-j)/sqrt((n-i)(n-i+1)), x against the planted
+                 solution, the residual.  A failed check makes the process exit non-zero.
+  cpu_baseline = the UNMODIFIED reference (oracle/_ref/ref_time: cholesky_decomp, then compute_y +
+                 compute_x, wall clock) on the box's host cores through the minimpi shim; at the
+                 same n for c2 / c3, on a bounded sample (n = 16384, same generator and m) above
 `--impl reference` prints the same line for the reference's CPU path alone.
 """
 import argparse
@@ -104,18 +114,22 @@ def host_cores():
 
 
 def run_reference_sample(n, m, cores):
-    """One run of the unmodified reference CLI on `cores` minimpi ranks; returns its `elapsed`."""
-    exe = os.path.join(ROOT, "oracle", "_ref", "test_mat_ref")
+    """One run of the unmodified reference (oracle/_ref/ref_time: the reference's own functions in the
+    order of test/test_mat.cpp) on `cores` minimpi ranks; factor and solve wall clock."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_time")
     if not os.path.exists(exe):
-        return None, "oracle/_ref/test_mat_ref not built (needs /root/reference at build time)"
+        return None, "oracle/_ref/ref_time not built (needs /root/reference at build time)"
     env = dict(os.environ, MINIMPI_NP=str(cores))
     cwd = os.path.join(ROOT, "gpurun_out")
     os.makedirs(cwd, exist_ok=True)
     p = subprocess.run([exe, str(n), str(m)], capture_output=True, text=True, env=env, cwd=cwd)
-    mm = re.search(r"residual = (\S+), er = (\S+), elapsed = (\S+) sec", p.stdout)
-    if p.returncode != 0 or not mm:
+    try:
+        d = json.loads(p.stdout.strip().splitlines()[-1])
+    except (ValueError, IndexError):
+        d = None
+    if p.returncode != 0 or not d or d.get("failed"):
         return None, f"reference run failed rc={p.returncode}: {p.stdout[-200:]} {p.stderr[-200:]}"
-    return {"elapsed": float(mm.group(3)), "residual": float(mm.group(1)), "error": float(mm.group(2))}, None
+    return {"elapsed": d["factor_s"], "solve": d["solve_s"], "residual": d["residual"], "error": d["error"]}, None
 
 
 def run_oracle_port_sample(n, m):
@@ -144,12 +158,15 @@ def run_oracle_port_sample(n, m):
     el = time.perf_counter() - t0
     if fail:
         return None, "oracle port reported a numerical failure"
-    return {"elapsed": el, "residual": None, "error": None}, None
+    return {"elapsed": el, "solve": None, "residual": None, "error": None}, None
 
 
-def reference_sample_size(n_full):
-    """Bounded sample: same generator and m, n shrunk so one CPU factor takes ~10-30 s."""
-    return min(n_full, int(os.environ.get("MS_BENCH_REF_N", "8192")))
+def reference_sample_size(n_full, repeated):
+    """Bounded sample: same generator and m; the same n up to 16384 (about 20 s of CPU work per run on
+    16 cores), n = 16384 above that.  The reference ARM repeats the run steps + warmup times, so its
+    bound is n = 8192 (about 5 s per run) unless MS_BENCH_REF_N says otherwise."""
+    cap = int(os.environ.get("MS_BENCH_REF_N", "8192" if repeated else "16384"))
+    return min(n_full, cap)
 
 
 def reference_arm(args):
@@ -157,11 +174,11 @@ def reference_arm(args):
     if rank != 0:
         return 0  # the other ranks of a torchrun launch have nothing to do
     cores = host_cores()
-    ns = reference_sample_size(args.n)
+    ns = reference_sample_size(args.n, repeated=True)
     kind = "reference"
-    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "test_mat_ref")):
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_time")):
         kind, cores, ns = "port", 1, min(ns, 2048)
-    times, last = [], None
+    times, solves, last = [], [], None
     for it in range(args.warmup + args.steps):
         if kind == "reference":
             r, err = run_reference_sample(ns, args.m, cores)
@@ -173,11 +190,13 @@ def reference_arm(args):
         last = r
         if it >= args.warmup:
             times.append(r["elapsed"])
+            solves.append(r["solve"])
     t = sum(times) / len(times)
+    solve_ms = sum(solves) / len(solves) * 1e3 if all(v is not None for v in solves) else None
     gf = ns ** 3 / 3.0 / t / 1e9
     if kind == "reference":
-        sample = (f"formula A_ij=n-max(i,j), n={ns}, m={args.m}: reference CPU factor "
-                  f"(its own `elapsed` timer), {cores} minimpi ranks on the box's host cores")
+        sample = (f"formula A_ij=n-max(i,j), n={ns}, m={args.m}: unmodified reference, cholesky_decomp wall clock "
+                  f"(what its own `elapsed` covers), {cores} minimpi ranks on the box's host cores")
     else:
         sample = (f"formula A_ij=n-max(i,j), n={ns}, m={args.m}: oracle/ms_oracle.c (C restatement of the "
                   f"reference, one host thread) because oracle/_ref was not shipped")
@@ -187,8 +206,10 @@ def reference_arm(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"formula SPD n={args.n} m={args.m}; reference timed on the bounded sample n={ns}",
                    "n": args.n, "m": args.m, "sample_n": ns},
-        "cpu_baseline": {"value": gf, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": gf, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "solve_ms": solve_ms},
         "e2e": {"value": gf, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "factor_ms": t * 1e3, "solve_ms": solve_ms, "same_n_as_workload": ns == args.n,
         "residual_abs": last["residual"], "error_abs": last["error"],
     }
     print(json.dumps(line))
@@ -196,11 +217,44 @@ def reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- our arm
+def dgemm_yardstick():
+    """cuBLAS Dgemm 8192^3 through torch.matmul: burst (best of 5) and 4 s back to back.  A library
+    reference for "how good is the DMMA kernel", not a denominator."""
+    import torch
+    try:
+        a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+        b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+        torch.matmul(a, b)
+        torch.cuda.synchronize()
+        flops = 2.0 * 8192 ** 3
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            e1.synchronize()
+            best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(4, int(4.0 / (flops / (best * 1e12))))
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        sustained = reps * flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        del a, b
+        torch.cuda.empty_cache()
+        return {"burst_tflops": best, "sustained_tflops": sustained}
+    except Exception as exc:  # noqa: BLE001 - a yardstick must never break the bench
+        return {"error": str(exc)[:120]}
+
+
 def our_arm(args):
     import numpy as np
     import torch
     import matrix_solver_b200 as ms
-    from matrix_solver_b200 import dist, layout
+    from matrix_solver_b200 import dist, layout, selfcheck
 
     rank, local, world = dist.env_rank()
     if world != args.gpus:
@@ -222,6 +276,7 @@ def our_arm(args):
     solver.set_option("profile_update", 1)
 
     peak_dmma = ms.probe_dmma_peak(local) if rank == 0 else 0.0
+    dgemm = dgemm_yardstick() if (rank == 0 and not args.no_dgemm) else None
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -250,8 +305,9 @@ def our_arm(args):
         sampler.start()
     st0 = solver.stats()
     acc = {k: 0.0 for k in ("factor_ms", "forward_ms", "backward_ms", "init_ms", "bnorm_ms", "update_ms",
-                            "update_flops")}
+                            "update_sum_ms", "update_flops")}
     any_fail = False
+    norm = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         norm, failed = step()
@@ -263,11 +319,18 @@ def our_arm(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     st1 = solver.stats()
+    forward_fused = bool(st1["forward_fused"])
 
-    # correctness evidence of the last step: residual with the regenerated matrix
+    # ---- parity of the last step (outside the timed region; collective: every rank takes part)
+    parity = selfcheck.check_parity(solver, n, m, world, norm, any_fail)
+    # residual with the regenerated matrix (the factor overwrote A, test/test_mat.cpp:149-160)
     solver.init_formula(0)
     resid, err = solver.residual()
     bnorm2 = float(np.linalg.norm(solver.get_vec("b")))
+    parity["residual_rel"] = resid / bnorm2 if bnorm2 else None
+    parity["residual_tol_rel"] = 1e-13
+    parity["ok"] = bool(parity["ok"] and bnorm2 > 0 and resid / bnorm2 <= 1e-13)
+    parity_ok_all = dist.max_over_ranks(0.0 if parity["ok"] else 1.0) == 0.0
 
     K = args.steps
     factor_ms = dist.max_over_ranks(acc["factor_ms"] / K)
@@ -276,10 +339,12 @@ def our_arm(args):
     bwd_ms = dist.max_over_ranks(acc["backward_ms"] / K)
     init_ms = dist.max_over_ranks(acc["init_ms"] / K)
     bnorm_ms = dist.max_over_ranks(acc["bnorm_ms"] / K)
-    upd_ms_rank = acc["update_ms"] / K
+    upd_ms_rank = acc["update_ms"] / K          # union of the launch intervals on this rank
+    upd_sum_ms_rank = acc["update_sum_ms"] / K
     upd_flops_rank = acc["update_flops"] / K
     upd_tflops_rank = upd_flops_rank / upd_ms_rank / 1e9 if upd_ms_rank > 0 else 0.0
     upd_tflops_min = -dist.max_over_ranks(-upd_tflops_rank)
+    upd_ms_max = dist.max_over_ranks(upd_ms_rank)
     launches = dist.sum_over_ranks(st1["kernel_launches"] - st0["kernel_launches"])
     value = layout.factor_flops(n) / (factor_ms * 1e-3) / 1e9
 
@@ -325,8 +390,9 @@ def our_arm(args):
             e2e = {"value": layout.factor_flops(n) / t_e2e / 1e9, "unit": UNIT,
                    "h2d_bytes_per_step": dist.sum_over_ranks((stx["h2d_bytes"] - h2d0) / len(e2e_times)),
                    "d2h_bytes_per_step": dist.sum_over_ranks((stx["d2h_bytes"] - d2h0) / len(e2e_times)),
-                   "seconds": t_e2e, "x_err_vs_planted": float(np.linalg.norm(x - (np.arange(n) % 2 == 0))),
-                   "what": "pinned host rows -> ms_upload_rows -> b/norm -> factor -> forward -> backward -> D2H x, d"}
+                   "seconds": t_e2e, "steps": len(e2e_times),
+                   "x_err_vs_planted": float(np.linalg.norm(x - (np.arange(n) % 2 == 0))),
+                   "what": "pinned host rows -> ms_upload_rows -> b/norm -> factor (+ fused forward) -> backward -> D2H x, d"}
             pin.free()
 
         except (ms.MSError, MemoryError) as exc:  # e.g. not enough page-lockable host memory
@@ -336,18 +402,20 @@ def our_arm(args):
     solver.close()
     if rank != 0:
         dist.shutdown()
-        return 0
+        return 0 if parity_ok_all else 3
 
     # ---- cpu baseline (rank 0, N = 1 only): the reference on the host cores, bounded sample
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = host_cores()
-        ns = reference_sample_size(n)
+        ns = reference_sample_size(n, repeated=False)
         r, errmsg = run_reference_sample(ns, m, cores)
         if r:
             cpu = {"value": ns ** 3 / 3.0 / r["elapsed"] / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": f"formula n={ns}, m={m}: unmodified reference CPU factor, {cores} minimpi ranks, "
-                             f"{r['elapsed']:.2f} s (its own elapsed timer); residual {r['residual']:.3e}"}
+                   "solve_ms": r["solve"] * 1e3, "factor_ms": r["elapsed"] * 1e3, "same_n_as_workload": ns == n,
+                   "sample": f"formula n={ns}, m={m}: unmodified reference (oracle/_ref/ref_time), {cores} minimpi "
+                             f"ranks: cholesky_decomp {r['elapsed']:.2f} s, compute_y + compute_x {r['solve']:.3f} s; "
+                             f"residual {r['residual']:.3e}"}
         else:
             ns = min(ns, 2048)
             r, err2 = run_oracle_port_sample(ns, m)
@@ -358,49 +426,69 @@ def our_arm(args):
             else:
                 cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": errmsg}
 
-    traffic = None
+    # DRAM traffic of the dominant kernel: one `ncu --set full` capture of ONE launch (the step-0 bulk
+    # update of this n, m on one GPU), regenerated by tools/ncu_traffic.sh; quoted only for the
+    # configuration it was captured on
+    traffic, traffic_note = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "update_kernel_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        if world == 1 and tj.get("n") == n and tj.get("m") == m:
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = {k: tj.get(k) for k in ("launch", "algorithmic_bytes_per_launch", "duration_ms_under_ncu",
+                                                   "dmma_pipe_active_pct", "source")}
     except (OSError, ValueError):
         pass
+    peak_src = ("measured in this run: register-only DMMA.8x8x4 issue loop on all SMs (ms_probe_dmma_peak) = "
+                f"{peak_dmma:.2f} TFLOP/s; MEASURED_PEAKS.json has no fp64 entry; nominal 37 TFLOP/s")
+    if dgemm and "burst_tflops" in dgemm:
+        peak_src += (f"; library yardstick (not the denominator): cuBLAS Dgemm 8192^3 "
+                     f"{dgemm['burst_tflops']:.2f} burst / {dgemm['sustained_tflops']:.2f} sustained TFLOP/s")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": wall_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"formula-generated SPD A_ij=n-max(i,j), n={n}, block m={m}, factor+solve "
-                               f"(BASELINE configs[4]); block-row cyclic over {world} GPU(s)",
+                               f"(BASELINE configs[{CONFIG_INDEX.get((n, m), '-')}]); block-row cyclic over {world} GPU(s)",
                    "n": n, "m": m,
                    "parallelism": f"block-row-cyclic x{world}, look-ahead 2, panel over NVLink peer memory "
                                   f"(copy engines; ncclBroadcast when MS_P2P=0)" if world > 1 else "single GPU, look-ahead 2",
-                   "kernel_variants": {"tile": int(os.environ.get("MS_TILE_VARIANT", "1")),
-                                       "diag": int(os.environ.get("MS_DIAG_VARIANT", "1"))},
+                   "forward_solve": "fused into the factorisation (b as augmented column)" if forward_fused
+                                    else "separate sweep",
                    "l2": "inputs larger than L2 (matrix %.1f GB per GPU)" % (8.0 * n * n / world / 1e9)},
         "factor_ms": factor_ms, "forward_ms": fwd_ms, "backward_ms": bwd_ms, "solve_ms": fwd_ms + bwd_ms,
         "init_ms": init_ms, "bnorm_ms": bnorm_ms,
         "time_to_solution_ms": init_ms + bnorm_ms + factor_ms + fwd_ms + bwd_ms,
         "residual_abs": resid, "residual_rel": resid / bnorm2 if bnorm2 else None, "error_abs": err,
-        "numerical_failure": bool(any_fail),
+        "numerical_failure": bool(any_fail), "parity": parity,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "tile_dmma_kernel<UPDATE> (fp64 DMMA.8x8x4 trailing update)",
                      "achieved": upd_tflops_min, "peak": peak_dmma, "unit": "TFLOP/s",
                      "frac": upd_tflops_min / peak_dmma if peak_dmma else None, "traffic": traffic,
-                     "peak_source": "measured in this run: register-only DMMA.8x8x4 issue loop on all SMs "
-                                    "(ms_probe_dmma_peak); MEASURED_PEAKS.json has no fp64 entry; nominal 37 TFLOP/s",
-                     "algorithmic_flops_per_step": dist_safe(upd_flops_rank),
-                     "kernel_ms_per_step": upd_ms_rank,
-                     "whole_factor_frac_of_peak": value / 1e3 / peak_dmma if peak_dmma else None,
+                     "traffic_capture": traffic_note,
+                     "peak_source": peak_src, "dgemm_yardstick": dgemm,
+                     "algorithmic_flops_per_step": float(upd_flops_rank),
+                     "kernel_ms_per_step": upd_ms_max,
+                     "kernel_ms_per_step_is": "union of the update launches' CUDA-event intervals (max over ranks); "
+                                              "<= factor_ms by construction",
+                     "kernel_ms_sum_of_launches": upd_sum_ms_rank,
+                     "whole_factor_frac_of_peak": value / 1e3 / (peak_dmma * world) if peak_dmma else None,
                      "hbm_peak_gbs": peaks.get("hbm_gbs"),
-                     "solve_achieved_gbs": layout.solve_bytes(n) * 2 / ((fwd_ms + bwd_ms) * 1e-3) / 1e9},
+                     "backward_achieved_gbs": layout.solve_bytes(n) / (bwd_ms * 1e-3) / 1e9 if bwd_ms else None,
+                     "backward_frac_of_hbm": (layout.solve_bytes(n) / (bwd_ms * 1e-3) / 1e9 / (peaks["hbm_gbs"] * world)
+                                              if bwd_ms and peaks.get("hbm_gbs") else None)},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     dist.shutdown()
+    if not parity_ok_all:
+        print("bench.py: PARITY CHECK FAILED: " + json.dumps(parity), file=sys.stderr)
+        return 3
     return 0
 
 
-def dist_safe(v):
-    return float(v)
+CONFIGS = {"c2": (4096, 64), "c3": (16384, 128), "c4": (32768, 256), "c5": (65536, 256)}
+CONFIG_INDEX = {(4096, 64): 1, (16384, 128): 2, (32768, 256): 3, (65536, 256): 4}
 
 
 def main():
@@ -409,12 +497,17 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("MS_BENCH_N", "65536")))
-    ap.add_argument("--m", type=int, default=int(os.environ.get("MS_BENCH_M", "256")))
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--config", default=os.environ.get("MS_BENCH_CONFIG", "c5"), choices=sorted(CONFIGS))
+    ap.add_argument("--n", type=int, default=int(os.environ.get("MS_BENCH_N", "0")))
+    ap.add_argument("--m", type=int, default=int(os.environ.get("MS_BENCH_M", "0")))
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dgemm", action="store_true")
     args = ap.parse_args()
+    cn, cm = CONFIGS[args.config]
+    args.n = args.n or cn
+    args.m = args.m or cm
     if args.impl == "reference":
         return reference_arm(args)
     return our_arm(args)

@@ -46,9 +46,9 @@ enum { MS_FORMULA_F1 = 0, MS_FORMULA_HILBERT = 1 };
 typedef struct ms_stats
 {
   double factor_ms;       /* device time of the last ms_factor (CUDA events) */
-  double update_ms;       /* summed device time of the rank-m trailing-update launches (0 unless
-                             ms_set_option(ctx, "profile_update", 1)); with look-ahead two of
-                             them can run concurrently, so the sum over-counts wall time */
+  double update_ms;       /* device time in which at least one rank-m trailing-update launch was running:
+                             the UNION of the launch intervals (0 unless ms_set_option(ctx,
+                             "profile_update", 1)); never exceeds factor_ms */
   double forward_ms;      /* last ms_solve_forward */
   double backward_ms;     /* last ms_solve_backward */
   double init_ms;         /* last ms_init_formula / upload */
@@ -59,6 +59,9 @@ typedef struct ms_stats
   long long update_launches; /* trailing-update launches in the last ms_factor */
   long long h2d_bytes, d2h_bytes; /* bytes moved across PCIe since ms_create */
   int used_dmma;          /* 1 if the DMMA/TMA tile kernel ran in the last factor */
+  int forward_fused;      /* 1 if the last ms_solve_forward only read back the y that ms_factor carried
+                             along as an augmented column (no sweep over R) */
+  double update_sum_ms;   /* plain sum of the same intervals (look-ahead lets two of them overlap) */
 } ms_stats;
 
 /* ---- library / error state -------------------------------------------------- */

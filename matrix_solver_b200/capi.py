@@ -26,6 +26,8 @@ class Stats(C.Structure):
         ("residual_ms", C.c_double), ("update_flops", C.c_double),
         ("kernel_launches", C.c_longlong), ("update_launches", C.c_longlong),
         ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("used_dmma", C.c_int),
+        ("forward_fused", C.c_int),
+        ("update_sum_ms", C.c_double),
     ]
 
     def as_dict(self):

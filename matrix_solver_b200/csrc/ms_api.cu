@@ -134,6 +134,8 @@ ctx_free (ms_ctx *c)
     cudaFreeHost (c->h_pinned);
   for (auto e : c->ev_pool)
     cudaEventDestroy (e);
+  for (auto e : c->prof_pool)
+    cudaEventDestroy (e);
   if (c->ev_t0)
     cudaEventDestroy (c->ev_t0);
   if (c->ev_t1)
@@ -174,7 +176,8 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   c->rank = rank;
   c->nranks = nranks;
   c->nblocks = n / m + (n % m > 0);
-  c->ld = round_up (n, MS_CHUNK);
+  c->ld = round_up (n + 1, MS_CHUNK);  // + the augmented column (b during the factorisation)
+  c->ncols = n + 1;
   c->hpb = round_up (m, MS_SUB);
   c->fast = (m % MS_SUB == 0 && m <= 1024);  // the tile kernel keeps K = m sign words in shared memory
   c->rows_local = 0;
@@ -270,6 +273,9 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   e = getenv ("MS_PANEL_GEMM");
   if (e && atoi (e))
     c->panel_trsm = false;
+  e = getenv ("MS_FUSE_FORWARD");
+  if (e && !atoi (e))
+    c->fuse_forward = false;
   e = getenv ("MS_NO_LOOKAHEAD");
   if (e && atoi (e))
     c->lookahead = false;
@@ -292,11 +298,22 @@ ms_set_option (ms_ctx *c, const char *key, long value)
   else if (!strcmp (key, "lookahead"))
     c->lookahead = value != 0;
   else if (!strcmp (key, "profile_update"))
-    c->profile_update = value != 0;
+    {
+      c->profile_update = value != 0;
+      MS_CUDA (cudaSetDevice (c->device));
+      if (c->profile_update && c->prof_pool.empty ())
+        {
+          c->prof_pool.resize (2 * (4 * c->nblocks + 8));
+          for (auto &e : c->prof_pool)
+            MS_CUDA (cudaEventCreate (&e));
+        }
+    }
   else if (!strcmp (key, "panel_trsm"))
     c->panel_trsm = value != 0;
   else if (!strcmp (key, "single_launch_sweeps"))
     c->no_sweep = value == 0;
+  else if (!strcmp (key, "fuse_forward"))
+    c->fuse_forward = value != 0;
   else if (!strcmp (key, "tile_tma3"))
     c->tm3_state = value ? 0 : -1;  // 0 = encode the rank-3 maps on the next update launch
   else
@@ -604,8 +621,22 @@ ms_set_vec (ms_ctx *c, int which, const double *host, size_t count)
 {
   MS_CHECK_ARG (c && host && which >= 0 && which < 5 && count <= c->n, "bad argument");
   MS_CUDA (cudaSetDevice (c->device));
+  if (which == MS_VEC_B && c->b_version_factored == c->b_version && count == c->n)
+    {
+      // the mirrored compute_y hands back the b that init_b_get_norm produced (test/test_mat.cpp:114,132):
+      // if these are the very bits the factorisation already carried through, the fused forward solve
+      // stays valid and nothing has to be written
+      std::vector<double> cur (count);
+      MS_CUDA (cudaMemcpyAsync (cur.data (), c->vec[which], count * sizeof (double), cudaMemcpyDeviceToHost, c->s_main));
+      MS_CUDA (cudaStreamSynchronize (c->s_main));
+      c->stats.d2h_bytes += (long long)(count * sizeof (double));
+      if (memcmp (cur.data (), host, count * sizeof (double)) == 0)
+        return MS_OK;
+    }
   MS_CUDA (cudaMemcpyAsync (c->vec[which], host, count * sizeof (double), cudaMemcpyHostToDevice, c->s_main));
   MS_CUDA (cudaStreamSynchronize (c->s_main));
+  if (which == MS_VEC_B)
+    c->b_version++;
   c->stats.h2d_bytes += (long long)(count * sizeof (double));
   return MS_OK;
 }
@@ -628,6 +659,7 @@ ms_b_and_norm (ms_ctx *c, double *norm)
   MS_CHECK_ARG (c && norm, "null argument");
   MS_CUDA (cudaSetDevice (c->device));
   phase_timer t (c, &c->stats.bnorm_ms);
+  c->b_version++;
   MS_TRY (ms_k_sym_rows (c, MS_SYM_BNORM, nullptr, c->vec[MS_VEC_B], nullptr, c->s_main));
   double *absp = ms_sym_abs_partial (c);
   if (c->nranks > 1)
@@ -708,9 +740,9 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s, cu
           // K1 then K3 as a triangular solve: no explicit inverse on the critical path
           MS_TRY (ms_k_diag (c, blk, c->ld, pc.h, thresh, c->vec[MS_VEC_D] + pc.row0, nullptr, nullptr, pre, c->ld,
                              pre_count, s));
-          if (col_lo >= c->n)
+          if (col_lo >= c->ncols)
             continue;
-          MS_TRY (ms_k_trsm_panel (c, blk, c->ld, rows, c->ld, pc.h, col_lo, c->n, c->vec[MS_VEC_D] + pc.row0,
+          MS_TRY (ms_k_trsm_panel (c, blk, c->ld, rows, c->ld, pc.h, col_lo, c->ncols, c->vec[MS_VEC_D] + pc.row0,
                                    c->PB[pb], c->hpb, k0, s));
         }
       else
@@ -718,7 +750,7 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s, cu
           // the reference's formulation: K1 + K2 (inverse) then K3 = (V D)^T * rows
           MS_TRY (ms_k_diag (c, blk, c->ld, pc.h, thresh, c->vec[MS_VEC_D] + pc.row0, c->Wt, nullptr, pre, c->ld,
                              pre_count, s));
-          if (col_lo >= c->n)
+          if (col_lo >= c->ncols)
             continue;
           if (tiles && pc.h == MS_SUB)
             MS_TRY (ms_k_tile_panel (c, pb, pc, I, s));
@@ -729,7 +761,7 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s, cu
               W.ld = 0;
               W.H = MS_SUB;
               MS_TRY (ms_k_generic_panel (c, W, rows, c->ld, rows, c->ld, pc.h, col_lo, c->PB[pb], c->hpb, k0,
-                                          c->n, s));
+                                          c->ncols, s));
             }
         }
       // later pieces of the same block row (their rows must have received the previous panel: the
@@ -773,8 +805,13 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
   c->stats.update_ms = 0;
   c->stats.used_dmma = 0;
   MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), sm));
-  std::vector<cudaEvent_t> prof;
   MS_CUDA (cudaEventRecord (c->ev_t0, sm));
+  // forward solve fused into the factorisation: the current b becomes column n of the matrix and comes
+  // out as z = D y; ms_solve_forward then only has to read it back
+  c->ncols = c->n + (c->fuse_forward ? 1 : 0);
+  c->b_version_factored = 0;
+  if (c->fuse_forward)
+    MS_TRY (ms_k_aug_scatter (c, c->vec[MS_VEC_B], sm));
   cudaEvent_t *ev_panel = c->ev_pool.data ();            // panel I factored (and received)
   cudaEvent_t *ev_strip = ev_panel + nb + 2;              // block row I updated through panel I-1
   cudaEvent_t *ev_u2a = ev_strip + nb + 2;                // block row I updated through panel I-2
@@ -786,18 +823,17 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
       MS_CUDA (cudaStreamWaitEvent (sp, ev_strip[0], 0));
       MS_CUDA (cudaStreamWaitEvent (su, ev_strip[0], 0));
     }
+  // profile_update: every update launch sits between two timing events taken from a pool that
+  // ms_set_option created (nothing is created or destroyed inside the factorisation)
+  size_t prof_used = 0;
   auto timed = [&] (cudaStream_t st, size_t I, int pb, size_t lr0, size_t lr1) -> int {
     const int K = (int)c->m;  // block row I is full whenever later block rows exist
-    if (!c->profile_update)
+    if (!c->profile_update || prof_used + 2 > c->prof_pool.size () || lr1 <= lr0)
       return do_update (c, pb, I, lr0, lr1, K, 0, st, true);
-    cudaEvent_t a, b;
-    MS_CUDA (cudaEventCreate (&a));
-    MS_CUDA (cudaEventCreate (&b));
-    MS_CUDA (cudaEventRecord (a, st));
+    MS_CUDA (cudaEventRecord (c->prof_pool[prof_used], st));
     int r = do_update (c, pb, I, lr0, lr1, K, 0, st, true);
-    MS_CUDA (cudaEventRecord (b, st));
-    prof.push_back (a);
-    prof.push_back (b);
+    MS_CUDA (cudaEventRecord (c->prof_pool[prof_used + 1], st));
+    prof_used += 2;
     return r;
   };
   auto mine = [&] (size_t J) { return J < nb && c->owner_of_block (J) == c->rank; };
@@ -887,14 +923,36 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
   c->stats.factor_ms = ms;
   if (elapsed_s)
     *elapsed_s = ms * 1e-3;
-  for (size_t i = 0; i + 1 < prof.size (); i += 2)
+  // device time in which at least one update launch was running: the union of the launch intervals
+  // (two launches overlap under look-ahead, so their plain sum over-counts wall time)
+  c->stats.update_sum_ms = 0;
+  if (prof_used)
     {
-      float t = 0;
-      MS_CUDA (cudaEventElapsedTime (&t, prof[i], prof[i + 1]));
-      c->stats.update_ms += t;
+      std::vector<std::pair<float, float>> iv (prof_used / 2);
+      for (size_t i = 0; i < prof_used; i += 2)
+        {
+          float a = 0, b = 0;
+          MS_CUDA (cudaEventElapsedTime (&a, c->ev_t0, c->prof_pool[i]));
+          MS_CUDA (cudaEventElapsedTime (&b, c->ev_t0, c->prof_pool[i + 1]));
+          iv[i / 2] = {a, b};
+          c->stats.update_sum_ms += b - a;
+        }
+      std::sort (iv.begin (), iv.end ());
+      double total = 0;
+      float lo = iv[0].first, hi = iv[0].second;
+      for (size_t i = 1; i < iv.size (); i++)
+        {
+          if (iv[i].first > hi)
+            {
+              total += hi - lo;
+              lo = iv[i].first;
+              hi = iv[i].second;
+            }
+          else
+            hi = std::max (hi, iv[i].second);
+        }
+      c->stats.update_ms = total + (hi - lo);
     }
-  for (auto e : prof)
-    cudaEventDestroy (e);
   if (c->trace && la)
     {
       c->trace_panel.assign (nb, -1.f);
@@ -913,6 +971,8 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
   int failed = c->h_flags[0] != 0;
   if (P > 1)
     MS_TRY (ms_nccl_agree_flag (c, &failed));
+  if (c->fuse_forward && !failed)
+    c->b_version_factored = c->b_version;
   return failed ? MS_NUMERICAL_FAILURE : MS_OK;
 }
 
@@ -940,6 +1000,21 @@ ms_solve_forward (ms_ctx *c, double norma)
   const double thresh = 1.e-14 * norma;
   cudaStream_t s = c->s_main;
   phase_timer t (c, &c->stats.forward_ms);
+  c->stats.forward_fused = 0;
+  if (c->b_version_factored != 0 && c->b_version_factored == c->b_version)
+    {
+      // the factorisation already carried this b through (augmented column): y = D z.  No pivot can
+      // fail here that ms_factor has not reported already (same |R_jj| < EPS*norm test, src/solver.cpp:195-199
+      // vs :122).  With several ranks every rank contributes its own rows and y is replicated like the
+      // reference's (MPI_Bcast per block, src/solver.cpp:204-205).
+      if (c->nranks > 1)
+        MS_CUDA (cudaMemsetAsync (c->vec[MS_VEC_Y], 0, c->ld * sizeof (double), s));
+      MS_TRY (ms_k_aug_gather (c, c->vec[MS_VEC_Y], s));
+      if (c->nranks > 1)
+        MS_TRY (ms_nccl_allreduce_sum (c, c->vec[MS_VEC_Y], c->n, s));
+      c->stats.forward_fused = 1;
+      return t.finish ();
+    }
   MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), s));
   MS_CUDA (cudaMemsetAsync (c->acc, 0, (c->ld + MS_SUB) * sizeof (double), s));
   if (c->nranks > 1)
@@ -1091,10 +1166,55 @@ blk_flag (ms_ctx *c, int *flag)
   return MS_OK;
 }
 
+// cholesky_decomp_U for blocks that do not fit one CTA's shared memory (w > 112; the BASELINE block sizes
+// 128 and 256 arrive here through the mirrored cholesky_decomp_U): one CTA works on the block in global
+// memory (it stays in L2), pivot by pivot, with the reference's roundings in the reference's order —
+// entry (k, j) loses (r_ik * r_ij) * d_i for i ascending, each product and difference rounded on its own,
+// then row k is divided by r_kk * d_k (src/solver.cpp:106-160).  Bit-identical to the oracle at every w;
+// speed is irrelevant here (the factorisation itself never factors more than 64 pivots per launch).
+__global__ void __launch_bounds__ (1024)
+diag_global_kernel (double *__restrict__ a, int w, double thresh, double *__restrict__ d_out, int *flags)
+{
+  const int tid = threadIdx.x;
+  // the reference tests the not-yet-updated a_ii of every pivot (src/solver.cpp:117)
+  for (int i = tid; i < w; i += 1024)
+    if (fabs (a[(size_t)i * w + i]) < thresh)
+      flags[0] = 1;
+  __syncthreads ();
+  for (int i = 0; i < w; i++)
+    {
+      double *ri = a + (size_t)i * w;
+      const double s = ri[i];
+      const double di = s > 0 ? 1.0 : -1.0;
+      const double rii = __dsqrt_rn (fabs (s));
+      const double den = __dmul_rn (rii, di);
+      __syncthreads ();  // everybody has read the pivot
+      if (tid == 0)
+        {
+          ri[i] = rii;
+          d_out[i] = di;
+          if (fabs (rii) < thresh)
+            flags[0] = 1;
+        }
+      for (int j = i + 1 + tid; j < w; j += 1024)
+        ri[j] = __ddiv_rn (ri[j], den);
+      __syncthreads ();
+      // rows k > i, columns j >= k
+      const int rem = w - i - 1;
+      for (int e = tid; e < rem * rem; e += 1024)
+        {
+          const int k = i + 1 + e / rem, j = i + 1 + e % rem;
+          if (j >= k)
+            a[(size_t)k * w + j] = __dsub_rn (a[(size_t)k * w + j], __dmul_rn (__dmul_rn (ri[k], ri[j]), di));
+        }
+      __syncthreads ();
+    }
+}
+
 extern "C" int
 ms_block_diag_factor (double *a_packed, double *d, int w, double norma)
 {
-  MS_CHECK_ARG (a_packed && d && w >= 1 && w <= 112, "bad argument (1 <= w <= 112)");
+  MS_CHECK_ARG (a_packed && d && w >= 1 && w <= 8192, "bad argument (1 <= w <= 8192)");
   ms_ctx *c;
   MS_TRY (blk_ctx (&c));
   std::vector<double> full ((size_t)w * w);
@@ -1105,7 +1225,14 @@ ms_block_diag_factor (double *a_packed, double *d, int w, double norma)
   cudaStream_t s = c->s_main;
   MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), s));
   MS_CUDA (cudaMemcpyAsync (da.p, full.data (), full.size () * 8, cudaMemcpyHostToDevice, s));
-  MS_TRY (ms_k_diag (c, da.p, w, w, 1.e-14 * norma, dd.p, nullptr, nullptr, da.p, w, w, s));
+  if (w <= 112)
+    MS_TRY (ms_k_diag (c, da.p, w, w, 1.e-14 * norma, dd.p, nullptr, nullptr, da.p, w, w, s));
+  else
+    {
+      diag_global_kernel<<<1, 1024, 0, s>>> (da.p, w, 1.e-14 * norma, dd.p, c->flags);
+      c->stats.kernel_launches++;
+      MS_CUDA (cudaGetLastError ());
+    }
   MS_CUDA (cudaMemcpyAsync (full.data (), da.p, full.size () * 8, cudaMemcpyDeviceToHost, s));
   MS_CUDA (cudaMemcpyAsync (d, dd.p, w * 8, cudaMemcpyDeviceToHost, s));
   int flag;
@@ -1157,10 +1284,38 @@ upper_inverse_kernel (const double *__restrict__ a, int w, double thresh, double
     }
 }
 
+// reverse_upper for w > 112: same recurrence and order as upper_inverse_kernel, operands in global memory
+// (one thread per column of the inverse; column j only ever reads its own earlier results)
+__global__ void __launch_bounds__ (256)
+upper_inverse_global_kernel (const double *__restrict__ a, int w, double thresh, double *__restrict__ inv, int *flags)
+{
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= w)
+    return;
+  if (fabs (a[(size_t)j * w + j]) < thresh)
+    flags[0] = 1;
+  for (int i = 0; i < j; i++)
+    inv[(size_t)j * w + i] = 0.0;  // strictly lower part of row j
+  for (int i = j; i >= 0; i--)
+    {
+      double val;
+      if (i == j)
+        val = __ddiv_rn (1.0, a[(size_t)i * w + i]);
+      else
+        {
+          double sum = 0;
+          for (int k = i + 1; k <= j; k++)
+            sum = __dadd_rn (sum, __dmul_rn (a[(size_t)i * w + k], inv[(size_t)k * w + j]));
+          val = __ddiv_rn (-sum, a[(size_t)i * w + i]);
+        }
+      inv[(size_t)i * w + j] = val;
+    }
+}
+
 extern "C" int
 ms_block_upper_inverse (const double *a_packed, double *inv_packed, int w, double norma)
 {
-  MS_CHECK_ARG (a_packed && inv_packed && w >= 1 && w <= 112, "bad argument (1 <= w <= 112)");
+  MS_CHECK_ARG (a_packed && inv_packed && w >= 1 && w <= 8192, "bad argument (1 <= w <= 8192)");
   ms_ctx *c;
   MS_TRY (blk_ctx (&c));
   std::vector<double> full ((size_t)w * w);
@@ -1171,9 +1326,14 @@ ms_block_upper_inverse (const double *a_packed, double *inv_packed, int w, doubl
   cudaStream_t s = c->s_main;
   MS_CUDA (cudaMemsetAsync (c->flags, 0, 8 * sizeof (int), s));
   MS_CUDA (cudaMemcpyAsync (da.p, full.data (), full.size () * 8, cudaMemcpyHostToDevice, s));
-  size_t smem = 2 * (size_t)w * (w + 1) * sizeof (double);
-  MS_CUDA (cudaFuncSetAttribute (upper_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  upper_inverse_kernel<<<1, 256, smem, s>>> (da.p, w, 1.e-14 * norma, di.p, c->flags);
+  if (w <= 112)
+    {
+      size_t smem = 2 * (size_t)w * (w + 1) * sizeof (double);
+      MS_CUDA (cudaFuncSetAttribute (upper_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      upper_inverse_kernel<<<1, 256, smem, s>>> (da.p, w, 1.e-14 * norma, di.p, c->flags);
+    }
+  else
+    upper_inverse_global_kernel<<<(w + 255) / 256, 256, 0, s>>> (da.p, w, 1.e-14 * norma, di.p, c->flags);
   c->stats.kernel_launches++;
   MS_CUDA (cudaGetLastError ());
   MS_CUDA (cudaMemcpyAsync (full.data (), di.p, full.size () * 8, cudaMemcpyDeviceToHost, s));
@@ -1228,7 +1388,7 @@ ms_block_panel (const double *inv_packed, double *A, const double *D, int h, int
 extern "C" int
 ms_block_trsm_panel (const double *r_packed, double *A, const double *D, int h, int w)
 {
-  MS_CHECK_ARG (r_packed && A && D && h >= 1 && h <= MS_SUB && w >= 1, "bad argument (1 <= h <= 64)");
+  MS_CHECK_ARG (r_packed && A && D && h >= 1 && w >= 1, "bad argument");
   ms_ctx *c;
   MS_TRY (blk_ctx (&c));
   std::vector<double> R ((size_t)h * h);
@@ -1243,9 +1403,60 @@ ms_block_trsm_panel (const double *r_packed, double *A, const double *D, int h, 
   MS_CUDA (cudaMemcpyAsync (dR.p, R.data (), R.size () * 8, cudaMemcpyHostToDevice, s));
   MS_CUDA (cudaMemcpyAsync (dA.p, A, (size_t)h * w * 8, cudaMemcpyHostToDevice, s));
   MS_CUDA (cudaMemcpyAsync (dD.p, D, h * 8, cudaMemcpyHostToDevice, s));
-  MS_TRY (ms_k_trsm_panel (c, dR.p, (size_t)h, dA.p, (size_t)w, h, 0, (size_t)w, dD.p, dPB.p, MS_SUB, 0, s));
+  // what the factorisation does inside a block row: 64-row piece t is solved against its own triangle,
+  // then the pieces below it lose R_tu^T D_t X_t (X_t = D_t R_tt^{-T}(...), so D_t X_t is the unscaled solve)
+  for (int t0 = 0; t0 < h; t0 += MS_SUB)
+    {
+      const int ht = std::min (MS_SUB, h - t0);
+      MS_TRY (ms_k_trsm_panel (c, dR.p + (size_t)t0 * h + t0, (size_t)h, dA.p + (size_t)t0 * w, (size_t)w, ht, 0,
+                               (size_t)w, dD.p + t0, dPB.p, MS_SUB, 0, s));
+      const int below = h - t0 - ht;
+      if (below > 0)
+        MS_TRY (ms_k_generic_block_update (c, dA.p + (size_t)(t0 + ht) * w, (size_t)w, dR.p + (size_t)t0 * h + t0 + ht,
+                                           (size_t)h, dD.p + t0, dA.p + (size_t)t0 * w, (size_t)w, ht, below, w, 0, s));
+    }
   MS_CUDA (cudaMemcpyAsync (A, dA.p, (size_t)h * w * 8, cudaMemcpyDeviceToHost, s));
   MS_CUDA (cudaStreamSynchronize (s));
+  return MS_OK;
+}
+
+// The same contraction on the DMMA / TMA tile kernel of the factorisation (k and h multiples of 64):
+// a throw-away context whose panel buffer holds P = [R1 | R2] (k x (h + w), chunk-major) and whose matrix
+// rows 0..h-1 hold A in columns [h, h + w) — one update launch then computes rows 0..h-1 of
+// C -= P^T D P, i.e. A -= R1^T D R2 in the columns we read back (the columns left of h receive
+// R1^T D R1, which nobody looks at).  For the packed-upper twin R2 == R1 and P = R1, C = A.
+static int
+block_update_dmma (double *A_full, const double *R1, const double *D, const double *R2, int k, int h, int w,
+                   int syrk)
+{
+  ms_ctx *b;
+  MS_TRY (blk_ctx (&b));
+  const size_t ncols = syrk ? (size_t)w : (size_t)h + (size_t)w;
+  const size_t col0 = syrk ? 0 : (size_t)h;
+  ms_ctx *t = nullptr;
+  MS_TRY (ms_create (&t, std::max (ncols, (size_t)k), (size_t)k, b->device, 0, 1, nullptr));
+  struct closer
+  {
+    ms_ctx *t;
+    ~closer () { ms_destroy (t); }
+  } guard{t};
+  t->ncols = ncols;
+  std::vector<double> pb (t->ld * t->hpb, 0.0);
+  for (int kk = 0; kk < k; kk++)
+    for (size_t j = 0; j < ncols; j++)
+      pb[chunk_major_index ((size_t)kk, j, t->hpb)]
+        = (syrk || j < (size_t)h) ? R1[(size_t)kk * h + j] : R2[(size_t)kk * w + (j - h)];
+  cudaStream_t s = t->s_main;
+  MS_CUDA (cudaMemcpyAsync (t->PB[0], pb.data (), pb.size () * 8, cudaMemcpyHostToDevice, s));
+  MS_CUDA (cudaMemcpyAsync (t->vec[MS_VEC_D], D, (size_t)k * 8, cudaMemcpyHostToDevice, s));
+  MS_CUDA (cudaMemcpy2DAsync (t->A + col0, t->ld * 8, A_full, (size_t)w * 8, (size_t)w * 8, (size_t)h,
+                              cudaMemcpyHostToDevice, s));
+  MS_TRY (ms_k_tile_update (t, 0, 0, 0, (size_t)h, k, 0, s));
+  MS_CUDA (cudaMemcpy2DAsync (A_full, (size_t)w * 8, t->A + col0, t->ld * 8, (size_t)w * 8, (size_t)h,
+                              cudaMemcpyDeviceToHost, s));
+  MS_CUDA (cudaStreamSynchronize (s));
+  b->stats.kernel_launches += t->stats.kernel_launches;
+  b->stats.used_dmma = 1;
   return MS_OK;
 }
 
@@ -1255,6 +1466,12 @@ block_update_common (double *A_full, size_t a_cnt, const double *R1, const doubl
 {
   ms_ctx *c;
   MS_TRY (blk_ctx (&c));
+  c->stats.used_dmma = 0;
+  // multiples of the tile kernel's piece height go to the DMMA kernel the factorisation runs
+  // (MS_BLOCK_GENERIC=1 keeps them on the DFMA kernel for comparison)
+  const char *g = getenv ("MS_BLOCK_GENERIC");
+  if (k % MS_SUB == 0 && h % MS_SUB == 0 && k <= 1024 && !(g && atoi (g)))
+    return block_update_dmma (A_full, R1, D, R2, k, h, w, upper_only);
   dev_buf dA, d1, d2, dD;
   MS_TRY (dA.alloc (a_cnt));
   MS_TRY (d1.alloc ((size_t)k * h));
@@ -1270,6 +1487,13 @@ block_update_common (double *A_full, size_t a_cnt, const double *R1, const doubl
   MS_CUDA (cudaMemcpyAsync (A_full, dA.p, a_cnt * 8, cudaMemcpyDeviceToHost, s));
   MS_CUDA (cudaStreamSynchronize (s));
   return MS_OK;
+}
+
+// debug hook (not in the public header): did the last ms_block_update(_diag) run on the DMMA tile kernel?
+extern "C" int
+ms_debug_block_used_dmma (void)
+{
+  return g_blk ? g_blk->stats.used_dmma : 0;
 }
 
 extern "C" int

@@ -79,7 +79,12 @@ struct ms_ctx
   size_t n = 0, m = 0;
   int device = 0, rank = 0, nranks = 1;
   size_t nblocks = 0;      // block rows: n/m + (n%m > 0)
-  size_t ld = 0;           // leading dimension (doubles), multiple of 16
+  size_t ld = 0;           // leading dimension (doubles), multiple of 16, >= n + 1
+  size_t ncols = 0;        // columns the factorisation kernels walk: n, or n + 1 when b rides along as
+                           // an augmented column (forward solve fused into the factorisation)
+  bool fuse_forward = true;
+  unsigned long long b_version = 1;           // bumped whenever vec[B] is rewritten
+  unsigned long long b_version_factored = 0;  // b_version the last ms_factor carried as its augmented column
   size_t rows_local = 0;   // rows stored on this rank
   size_t rows_alloc = 0;   // rows_local rounded up to MS_BM
   size_t hpb = 0;          // panel buffer chunk height: m rounded up to MS_SUB
@@ -106,6 +111,7 @@ struct ms_ctx
 
   cudaStream_t s_main = nullptr, s_panel = nullptr, s_row = nullptr;
   std::vector<cudaEvent_t> ev_pool;
+  std::vector<cudaEvent_t> prof_pool;  // timing events of "profile_update", created by ms_set_option
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 
   CUtensorMap tm_A, tm_PB[MS_NPB], tm_Wt;
@@ -262,6 +268,8 @@ int ms_k_get_col (ms_ctx *c, size_t j, double *d_out, cudaStream_t s);
 int ms_k_norms (ms_ctx *c, const double *r, const double *x, size_t n, double *d_out2,
                 cudaStream_t s);
 int ms_k_axpy_minus (ms_ctx *c, double *r, const double *b, size_t n, cudaStream_t s);
+int ms_k_aug_scatter (ms_ctx *c, const double *b, cudaStream_t s);
+int ms_k_aug_gather (ms_ctx *c, double *y, cudaStream_t s);
 
 // ms_kernels_diag.cu
 int ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_out,

@@ -55,6 +55,7 @@ struct tile_args
   size_t col_tile0;         // MODE_PANEL: first column tile (units of MS_BN)
   size_t col_lo_panel;      // MODE_PANEL: first column to write
   size_t n;                 // columns >= n are never written
+  size_t n_rows;            // rows >= n_rows do not exist (n < n_rows + 1 only without the augmented column)
   int tiles_per_cta;        // consecutive tiles one CTA walks before it retires
 };
 
@@ -88,7 +89,7 @@ __host__ __device__ __forceinline__ int
 tile_count_in_row (const tile_args &ta, int mode, int rt)
 {
   const size_t g = tile_row_global (ta, mode, rt);
-  if (g >= ta.n)
+  if (g >= ta.n_rows)
     return 0;
   const size_t total = (ta.n + MS_BN - 1) / MS_BN;
   const size_t first = tile_first_col_tile (ta, mode, g);
@@ -206,6 +207,51 @@ tile_consume (double (&acc)[2][2][2][2][2], uint32_t a_e0, uint32_t a_e1, uint32
             dmma_8x8x4 (acc[ib][jb][0][1][0], acc[ib][jb][0][1][1], fa[cur][ib].x, fb[cur][jb].y);
             dmma_8x8x4 (acc[ib][jb][1][0][0], acc[ib][jb][1][0][1], fa[cur][ib].y, fb[cur][jb].x);
             dmma_8x8x4 (acc[ib][jb][1][1][0], acc[ib][jb][1][1][1], fa[cur][ib].y, fb[cur][jb].y);
+          }
+    }
+}
+
+// the same chunk for a warp whose 32-column patch sticks out of the matrix on the right (the last
+// column tile: with the augmented column at index n only 1 of its 128 columns exists): only the
+// 16-column groups jb < njb that hold a real column are multiplied.  Off the hot path — no pipelining.
+template <int MODE>
+__device__ __forceinline__ void
+tile_consume_narrow (double (&acc)[2][2][2][2][2], uint32_t a_e0, uint32_t a_e1, uint32_t b_e0, uint32_t b_e1,
+                     uint32_t so, const uint32_t *sgn_chunk, bool any_neg, int njb)
+{
+#pragma unroll
+  for (int G = 0; G < 4; G++)
+    {
+      const int g = G >> 1, e = G & 1;
+      const uint32_t an = (e ? a_e1 : a_e0) + so + g * 1024;
+      const uint32_t bn = (e ? b_e1 : b_e0) + so + g * 1024;
+      double2 fa[2];
+#pragma unroll
+      for (int ib = 0; ib < 2; ib++)
+        fa[ib] = lds_f64x2 (an + ib * TILE_CHUNK_BYTES);
+      if (MODE == MS_MODE_UPDATE && any_neg)
+        {
+          const uint32_t sm = sgn_chunk[8 * g + e];
+#pragma unroll
+          for (int ib = 0; ib < 2; ib++)
+            {
+              fa[ib].x = flip_sign (fa[ib].x, sm);
+              fa[ib].y = flip_sign (fa[ib].y, sm);
+            }
+        }
+#pragma unroll
+      for (int jb = 0; jb < 2; jb++)
+        if (jb < njb)
+          {
+            const double2 fb = lds_f64x2 (bn + jb * TILE_CHUNK_BYTES);
+#pragma unroll
+            for (int ib = 0; ib < 2; ib++)
+              {
+                dmma_8x8x4 (acc[ib][jb][0][0][0], acc[ib][jb][0][0][1], fa[ib].x, fb.x);
+                dmma_8x8x4 (acc[ib][jb][0][1][0], acc[ib][jb][0][1][1], fa[ib].x, fb.y);
+                dmma_8x8x4 (acc[ib][jb][1][0][0], acc[ib][jb][1][0][1], fa[ib].y, fb.x);
+                dmma_8x8x4 (acc[ib][jb][1][1][0], acc[ib][jb][1][1][1], fa[ib].y, fb.y);
+              }
           }
     }
 }
@@ -437,9 +483,13 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const tile_pos tp = tile_decode<MODE> (ta, pref, n_rt, t);
       const size_t g_row0 = tp.g_row0;
       const size_t col0 = tp.ct * MS_BN;
-      const int rows_valid = g_row0 + MS_BM <= ta.n ? MS_BM : (int)(ta.n - g_row0);
+      const int rows_valid = g_row0 + MS_BM <= ta.n_rows ? MS_BM : (int)(ta.n_rows - g_row0);
       const size_t col_lo = (MODE == MS_MODE_UPDATE) ? g_row0 : ta.col_lo_panel;
       double *Ct = ta.C + (size_t)tp.rt * MS_BM * ta.ldc;
+      // 16-column groups of this warp's patch that hold at least one column < n (2 everywhere but in
+      // the last column tile)
+      const size_t wcol0 = col0 + (size_t)wn * 32;
+      const int njb = wcol0 + 16 < ta.n ? 2 : (wcol0 < ta.n ? 1 : 0);
       if (MODE == MS_MODE_UPDATE)
         {
           // the C tile is touched exactly once per launch and comes from HBM: start pulling this
@@ -512,7 +562,13 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
               mbar_wait (&full_bar[s], ph);
               const uint32_t *sgn_chunk = sgn + (kb4 + s) * MS_KC + 2 * q;
-              if (s == 0)
+              if (njb < 2)
+                {
+                  if (njb > 0)
+                    tile_consume_narrow<MODE> (acc, a_e0, a_e1, b_e0, b_e1, (uint32_t)s * TILE_STAGE_BYTES, sgn_chunk,
+                                               any_neg, njb);
+                }
+              else if (s == 0)
                 tile_consume<MODE, 0> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
               else if (s == 1)
                 tile_consume<MODE, 1> (acc, a_e0, a_e1, b_e0, b_e1, sgn_chunk, any_neg);
@@ -688,7 +744,8 @@ ms_k_tile_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_en
       ta.rank = c->rank;
       ta.nranks = c->nranks;
       ta.n_row_tiles = (int)((lr_end - lr + MS_BM - 1) / MS_BM);
-      ta.n = c->n;
+      ta.n = c->ncols;
+      ta.n_rows = c->n;
       int total = tile_total (ta, MS_MODE_UPDATE);
       if (total == 0)
         continue;
@@ -715,7 +772,7 @@ ms_k_tile_panel (ms_ctx *c, int pb, const ms_piece &pc, size_t I, cudaStream_t s
 {
   MS_CHECK_ARG (c->have_tm && pc.h == MS_SUB, "tile panel needs a full 64-row piece");
   size_t col_lo = pc.row0 + MS_SUB;
-  if (col_lo >= c->n)
+  if (col_lo >= c->ncols)
     return MS_OK;
   tile_args ta = {};
   ta.ax0 = 0; ta.axs = 0; ta.ay0 = 0; ta.ays = MS_SUB;
@@ -734,7 +791,8 @@ ms_k_tile_panel (ms_ctx *c, int pb, const ms_piece &pc, size_t I, cudaStream_t s
   ta.g0 = pc.row0;
   ta.col_tile0 = col_lo / MS_BN;
   ta.col_lo_panel = col_lo;
-  ta.n = c->n;
+  ta.n = c->ncols;
+  ta.n_rows = c->n;
   int total = tile_total (ta, MS_MODE_PANEL);
   if (total == 0)
     return MS_OK;
@@ -915,10 +973,10 @@ ms_k_generic_update (ms_ctx *c, ms_operand P, const double *dsign, size_t lrow_b
   ga.a_cols = c->n;
   ga.tri_mask = 1;
   ga.subtract = 1;
-  ga.n = c->n;
+  ga.n = c->ncols;
   ga.col_lo = 0;
   ga.col_begin = (g0 / 64) * 64;
-  size_t col_tiles = (c->n - ga.col_begin + 63) / 64;
+  size_t col_tiles = (c->ncols - ga.col_begin + 63) / 64;
   dim3 grid ((unsigned)col_tiles, (unsigned)((ga.rows + 63) / 64));
   gemm_generic_kernel<<<grid, 256, 0, s>>> (ga);
   LAUNCH_COUNT (c);

@@ -474,6 +474,58 @@ ms_k_get_col (ms_ctx *c, size_t j, double *d_out, cudaStream_t s)
   return MS_OK;
 }
 
+// ----------------------------------------------------------------------------- augmented column
+// Forward solve fused into the factorisation (replaces the separate pass of compute_y,
+// src/solver.cpp:162-208): b rides along as column n of the matrix.  The panel step turns it into
+// z_I = D_I R_II^{-T} (b_I - sum_{K<I} R_KI^T D_K z_K), the trailing update subtracts R_IJ^T D_I z_I
+// from b_J, so after the factorisation y = D z solves R^T y = b.
+__global__ void __launch_bounds__ (256)
+aug_scatter_kernel (double *__restrict__ A, size_t ld, size_t n, size_t m, size_t rows_local, int rank, int nranks,
+                    const double *__restrict__ b)
+{
+  size_t lr = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (lr >= rows_local)
+    return;
+  A[lr * ld + n] = b[global_row_of (lr, m, rank, nranks)];
+}
+
+// y_g = d_g * z_g for the rows this rank owns (the other entries of y are left alone: the caller
+// zeroes them and sums over the ranks)
+__global__ void __launch_bounds__ (256)
+aug_gather_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m, size_t rows_local, int rank,
+                   int nranks, const double *__restrict__ d, double *__restrict__ y)
+{
+  size_t lr = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (lr >= rows_local)
+    return;
+  size_t g = global_row_of (lr, m, rank, nranks);
+  y[g] = d[g] * A[lr * ld + n];
+}
+
+int
+ms_k_aug_scatter (ms_ctx *c, const double *b, cudaStream_t s)
+{
+  if (c->rows_local == 0)
+    return MS_OK;
+  aug_scatter_kernel<<<(unsigned)((c->rows_local + 255) / 256), 256, 0, s>>> (c->A, c->ld, c->n, c->m, c->rows_local,
+                                                                            c->rank, c->nranks, b);
+  LAUNCH_COUNT (c);
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
+int
+ms_k_aug_gather (ms_ctx *c, double *y, cudaStream_t s)
+{
+  if (c->rows_local == 0)
+    return MS_OK;
+  aug_gather_kernel<<<(unsigned)((c->rows_local + 255) / 256), 256, 0, s>>> (c->A, c->ld, c->n, c->m, c->rows_local,
+                                                                           c->rank, c->nranks, c->vec[MS_VEC_D], y);
+  LAUNCH_COUNT (c);
+  MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
 // ----------------------------------------------------------------------------- probes
 // Register-only DMMA issue loop: the fp64 tensor-pipe ceiling bench.py quotes fractions of.
 __global__ void __launch_bounds__ (256)

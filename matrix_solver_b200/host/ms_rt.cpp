@@ -2,7 +2,9 @@
 #include "ms_rt.h"
 
 #include <sched.h>
+#include <signal.h>
 #include <sys/mman.h>
+#include <sys/prctl.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -20,6 +22,8 @@ struct shared_page
   std::atomic<int> arrived;
   std::atomic<int> sense;
   std::atomic<int> id_ready;
+  std::atomic<int> abort_flag;             // a rank died: barrier spinners leave instead of waiting forever
+  std::atomic<unsigned long long> sum;     // scratch of ms_rt_sum
   char unique_id[MS_UNIQUE_ID_BYTES];
 };
 
@@ -35,6 +39,39 @@ struct problem
   size_t reserved_bytes;
 };
 std::map<double **, problem> g_problems;
+volatile sig_atomic_t g_kids_left = 0;
+
+// A rank that dies (ms_rt_die, a crash, an abort inside CUDA/NCCL) must not leave its peers spinning in
+// a barrier, inside an NCCL kernel or in cuStreamWaitValue32 for ever: every child dies with its parent
+// (PR_SET_PDEATHSIG), and the parent turns the first abnormal child exit into the end of the whole job.
+void
+kill_kids ()
+{
+  for (pid_t k : g_kids)
+    kill (k, SIGKILL);
+}
+
+void
+on_child_exit (int)
+{
+  int st;
+  pid_t pid;
+  while ((pid = waitpid (-1, &st, WNOHANG)) > 0)
+    {
+      if (g_kids_left > 0)
+        g_kids_left = g_kids_left - 1;
+      if (!(WIFEXITED (st) && WEXITSTATUS (st) == 0))
+        {
+          if (g_page)
+            g_page->abort_flag.store (1);
+          kill_kids ();
+          static const char msg[] = "matrix_solver_b200: a rank terminated abnormally; stopping all ranks\n";
+          ssize_t w = write (2, msg, sizeof (msg) - 1);
+          (void)w;
+          _exit (3);
+        }
+    }
+}
 
 size_t
 ref_alloc_elems (size_t n, size_t m, int rank, int size)
@@ -56,6 +93,10 @@ ms_rt_die (const char *what, int code)
   fflush (stdout);
   fprintf (stderr, "matrix_solver_b200: %s (code %d): %s\n", what, code, ms_last_error ());
   fflush (stderr);
+  if (g_page)
+    g_page->abort_flag.store (1);
+  if (g_rank == 0)
+    kill_kids ();  // the children of a dead rank 0 would be killed by PDEATHSIG anyway; do not wait for it
   _exit (3);
 }
 
@@ -79,6 +120,12 @@ ms_rt_init ()
         }
       g_page = new (p) shared_page ();
       fflush (nullptr);
+      struct sigaction sa;
+      memset (&sa, 0, sizeof (sa));
+      sa.sa_handler = on_child_exit;
+      sa.sa_flags = SA_RESTART | SA_NOCLDSTOP;
+      sigaction (SIGCHLD, &sa, nullptr);
+      const pid_t parent = getpid ();
       for (int r = 1; r < g_size; r++)
         {
           pid_t pid = fork ();  // must happen before the first CUDA call of the process
@@ -91,9 +138,14 @@ ms_rt_init ()
             {
               g_rank = r;
               g_kids.clear ();
+              signal (SIGCHLD, SIG_DFL);
+              prctl (PR_SET_PDEATHSIG, SIGKILL);
+              if (getppid () != parent)  // the parent died between fork and prctl
+                _exit (3);
               break;
             }
           g_kids.push_back (pid);
+          g_kids_left = g_kids_left + 1;
         }
     }
   return g_rank;
@@ -112,7 +164,30 @@ ms_rt_barrier ()
     }
   else
     while (g_page->sense.load () != g_local_sense)
-      sched_yield ();
+      {
+        if (g_page->abort_flag.load ())
+          {
+            fflush (stdout);
+            _exit (3);  // a peer died (ms_rt_die / crash): nobody will complete this barrier
+          }
+        sched_yield ();
+      }
+}
+
+// sum of one value per rank, the same on every rank afterwards (the reference's MPI_Reduce +
+// the root's check, test/test_mat.cpp:78-88, without needing a device)
+unsigned long long
+ms_rt_sum (unsigned long long v)
+{
+  if (g_size == 1)
+    return v;
+  ms_rt_barrier ();             // the previous round's reader has left
+  if (g_rank == 0)
+    g_page->sum.store (0);
+  ms_rt_barrier ();
+  g_page->sum.fetch_add (v);
+  ms_rt_barrier ();
+  return g_page->sum.load ();
 }
 
 void
@@ -136,11 +211,13 @@ ms_rt_finalize ()
     {
       ms_rt_barrier ();
       if (g_rank == 0)
-        for (pid_t k : g_kids)
-          {
-            int st;
-            waitpid (k, &st, 0);
-          }
+        {
+          // the SIGCHLD handler reaps; wait until every child is gone
+          while (g_kids_left > 0)
+            usleep (1000);
+          signal (SIGCHLD, SIG_DFL);
+          g_kids.clear ();
+        }
       else
         {
           fflush (nullptr);

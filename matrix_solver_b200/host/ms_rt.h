@@ -16,6 +16,7 @@ void ms_rt_finalize ();            // joins the sibling processes on rank 0
 int ms_rt_rank ();
 int ms_rt_size ();
 void ms_rt_barrier ();
+unsigned long long ms_rt_sum (unsigned long long v);  // all-reduce(sum) over the ranks, host side
 // the problem registered by alloc_rows for this rows_p array (nullptr if unknown)
 ms_ctx *ms_rt_ctx (double **rows_p);
 ms_ctx *ms_rt_bind (double **rows_p, size_t n, size_t m, double **token_out);

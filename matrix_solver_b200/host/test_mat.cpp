@@ -71,6 +71,12 @@ run (int argc, char **argv)
   double **rows_p = rows_holder.get ();
   const size_t my_elems = compute_alloc_size (n, m);
   std::unique_ptr<double[]> body (alloc_rows (n, m, my_elems, rows_p));
+  // the reference's allocation self-check (test/test_mat.cpp:78-88): the ranks' shares of the packed
+  // upper triangle must add up to n(n+1)/2
+  const size_t all_elems = (size_t)ms_rt_sum (my_elems);
+  if (ms_rt_rank () == root)
+    assert_and_do (all_elems == n * (n + 1) / 2,
+                   [=] { printf_root (root, "Allocated: %lu, wanted: %lu\n", all_elems, n * (n + 1) / 2); });
 
   if (!fill_matrix (rows_p, a))
     {

@@ -10,6 +10,10 @@
 //     oracle/ms_oracle.c and the CUDA path can be compared against it.  One problem
 //     size per process because the reference's gather_row keeps function-static
 //     buffers sized by its first call (src/init.cpp:313-329).
+//   * `ref_time n m`  (MS_REF_TIME_MAIN defined, the reference's Release flags): the TIMING harness of
+//     bench.py's CPU baseline.  Same call order, any number of minimpi ranks; wall-clock around
+//     cholesky_decomp (what the reference's own `elapsed` covers, test/test_mat.cpp:118-128) and
+//     around compute_y + compute_x (which the reference never times); prints one JSON line.
 //   * `libref_blocks.so`: extern "C" trampolines onto the reference's stateless block
 //     kernels (src/matrix_op.h:6-37, src/solver.h:14-15) for ctypes.
 //
@@ -202,6 +206,68 @@ main (int argc, char **argv)
   put (f, Atri.data (), Atri.size ());
   put (f, Rtri.data (), Rtri.size ());
   fclose (f);
+  MPI_Finalize ();
+  return 0;
+}
+#endif
+
+#ifdef MS_REF_TIME_MAIN
+#include <sys/time.h>
+static double
+now_s ()
+{
+  struct timeval tv;
+  gettimeofday (&tv, nullptr);
+  return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+int
+main (int argc, char **argv)
+{
+  MPI_Init (&argc, &argv);
+  if (argc < 3)
+    {
+      fprintf (stderr, "usage: %s n m\n", argv[0]);
+      return 2;
+    }
+  int rank = 0, size = 1;
+  MPI_Comm_rank (MPI_COMM_WORLD, &rank);
+  MPI_Comm_size (MPI_COMM_WORLD, &size);
+  size_t n = strtoul (argv[1], nullptr, 10);
+  size_t m = strtoul (argv[2], nullptr, 10);
+  size_t cols = n / m + (n % m > 0);
+  size_t alloc = compute_alloc_size (n, m);
+  std::vector<double *> rows_v (cols);
+  double **rows_p = rows_v.data ();
+  std::unique_ptr<double[]> body (alloc_rows (n, m, alloc, rows_p));
+  std::vector<double> b (n, 0.0), d (n, 0.0), y (n, 0.0), x (n, 0.0), r (n, 0.0);
+  init_mat (rows_p, n, m, formula_n_minus_max);
+  double norm = 0;
+  init_b_get_norm (b.data (), n, m, 0, rows_p, norm);
+  MPI_Bcast (b.data (), (int)n, MPI_DOUBLE, 0, MPI_COMM_WORLD);
+  MPI_Barrier (MPI_COMM_WORLD);
+  double t0 = now_s ();
+  bool fail = cholesky_decomp (rows_p, d.data (), n, m, norm);
+  MPI_Barrier (MPI_COMM_WORLD);
+  double t1 = now_s ();
+  bool f2 = fail || compute_y (rows_p, b.data (), y.data (), n, m, norm);
+  bool f3 = f2 || compute_x (rows_p, x.data (), y.data (), d.data (), n, m, norm, 0);
+  MPI_Barrier (MPI_COMM_WORLD);
+  double t2 = now_s ();
+  double resid = -1, err = -1;
+  if (!f3)
+    {
+      init_mat (rows_p, n, m, formula_n_minus_max);
+      find_disrep_vec (b.data (), x.data (), r.data (), n, m, 0, rows_p);
+      resid = norma_vec2 (r.data (), (int)n);
+      err = find_error (x.data (), (int)n);
+    }
+  if (rank == 0)
+    printf ("{\"n\": %zu, \"m\": %zu, \"ranks\": %d, \"factor_s\": %.6f, \"solve_s\": %.6f, \"failed\": %d, "
+            "\"residual\": %.6e, \"error\": %.6e}\n",
+            n, m, size, t1 - t0, t2 - t1, (int)f3, resid, err);
+  gather_row (0, 0, 0, 0, nullptr, nullptr, 1);
+  fflush (stdout);
   MPI_Finalize ();
   return 0;
 }

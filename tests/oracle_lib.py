@@ -303,3 +303,31 @@ def ref_dump(n, m, path=None, np_ranks=1):
         subprocess.run(cmd, check=True, env=env, stdout=subprocess.DEVNULL)
         raw = np.fromfile(out, dtype=np.float64)
     return parse_dump(raw, n)
+
+
+def compare_cli_output(got, want, case=""):
+    """The drop-in CLI against the reference's stdout: same tokens in the same order, text equal, numbers
+    compared as numbers (residual / er: same order of magnitude), `elapsed` ignored."""
+    import re
+    num = re.compile(r"-?\d+\.\d+(?:e[+-]\d+)?")
+    shape = re.compile(r"[ -]?\d+\.\d+(?:e[+-]\d+)?")    # a sign occupies the pad blank
+    gl, wl = got.strip().split("\n"), want.strip().split("\n")
+    assert len(gl) == len(wl), (case, got, want)
+    for a, b in zip(gl, wl):
+        a2, b2 = a.split(", elapsed")[0], b.split(", elapsed")[0]
+        # same tokens in the same order: text must match, numbers are compared as numbers
+        ta, tb = a2.split(), b2.split()
+        assert len(ta) == len(tb), (case, a, b)
+        for x, y in zip(ta, tb):
+            if num.fullmatch(x.rstrip(",")) and num.fullmatch(y.rstrip(",")):
+                continue
+            assert x == y, (case, a, b)
+        if "-" not in num.sub("", a2) + num.sub("", b2) and not re.search(r"\d-|\s-\d", a2 + b2):
+            # no minus signs anywhere: the column layout must be identical character by character
+            assert shape.sub("#", a2) == shape.sub("#", b2), (case, a, b)
+        fa, fb = [float(v) for v in num.findall(a2)], [float(v) for v in num.findall(b2)]
+        if "residual" in a2:
+            # n, m are integers (not matched); residual and er: same order of magnitude
+            assert fa[0] <= max(4 * fb[0], 1e-13) and fa[1] <= max(4 * fb[1], 1e-12), (case, a, b)
+        else:
+            assert np.allclose(fa, fb, rtol=2e-2, atol=1e-5), (case, a, b)

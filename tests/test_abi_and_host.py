@@ -124,6 +124,13 @@ def test_rank_runtime_forks_and_barriers(tmp_path):
         assert lines[-1] == f"rank 0 done, size {p}"
         rounds = [ln for ln in lines if ln.startswith("round")]
         assert rounds == [f"round {r} by rank {r % p} of {p}" for r in range(50)]
+    # a rank that dies must take the whole job down (exit 3) instead of leaving its peers in a barrier:
+    # once a child (SIGCHLD -> the parent stops everybody) and once rank 0 (children die with the parent)
+    for victim in (2, 0):
+        out = subprocess.run([str(exe), "die", str(victim)], env=dict(os.environ, MS_NGPU="4"), capture_output=True,
+                             text=True, timeout=60)
+        assert out.returncode == 3, (victim, out.returncode, out.stderr)
+        assert "simulated failure" in out.stderr
 
 
 def test_bench_reference_arm_contract(tmp_path):
