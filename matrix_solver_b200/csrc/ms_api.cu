@@ -176,8 +176,13 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   c->rank = rank;
   c->nranks = nranks;
   c->nblocks = n / m + (n % m > 0);
-  c->ld = round_up (n + 1, MS_CHUNK);  // + the augmented column (b during the factorisation)
-  c->ncols = n + 1;
+  // + the augmented column (b during the factorisation); MS_FUSE_FORWARD=0 at creation drops it from the
+  // layout altogether (A/B of the leading dimension: n = 65536 then has power-of-two rows again)
+  const char *ff = getenv ("MS_FUSE_FORWARD");
+  c->aug_cols = (ff && !atoi (ff)) ? 0 : 1;
+  c->fuse_forward = c->aug_cols > 0;
+  c->ld = round_up (n + (size_t)c->aug_cols, MS_CHUNK);
+  c->ncols = n + (size_t)c->aug_cols;
   c->hpb = round_up (m, MS_SUB);
   c->fast = (m % MS_SUB == 0 && m <= 1024);  // the tile kernel keeps K = m sign words in shared memory
   c->rows_local = 0;
@@ -223,6 +228,10 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
       CK (cudaMemset (c->vec[i], 0, (c->ld + MS_SUB) * sizeof (double)));
     }
   CK (cudaMalloc (&c->acc, (c->ld + MS_SUB) * sizeof (double)));
+  // epoch flags of the single-launch sweeps, one per 64-row piece (peers write into them when nranks > 1,
+  // so they exist before the IPC handles are exchanged)
+  CK (cudaMalloc (&c->sweep_ready, (c->pieces.size () + 8) * sizeof (int)));
+  CK (cudaMemset (c->sweep_ready, 0, (c->pieces.size () + 8) * sizeof (int)));
   CK (cudaMalloc (&c->flags, 8 * sizeof (int)));
   CK (cudaMemset (c->flags, 0, 8 * sizeof (int)));
   CK (cudaHostAlloc (&c->h_flags, 8 * sizeof (int), cudaHostAllocDefault));
@@ -273,9 +282,6 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   e = getenv ("MS_PANEL_GEMM");
   if (e && atoi (e))
     c->panel_trsm = false;
-  e = getenv ("MS_FUSE_FORWARD");
-  if (e && !atoi (e))
-    c->fuse_forward = false;
   e = getenv ("MS_NO_LOOKAHEAD");
   if (e && atoi (e))
     c->lookahead = false;
@@ -313,7 +319,7 @@ ms_set_option (ms_ctx *c, const char *key, long value)
   else if (!strcmp (key, "single_launch_sweeps"))
     c->no_sweep = value == 0;
   else if (!strcmp (key, "fuse_forward"))
-    c->fuse_forward = value != 0;
+    c->fuse_forward = value != 0 && c->aug_cols > 0;
   else if (!strcmp (key, "tile_tma3"))
     c->tm3_state = value ? 0 : -1;  // 0 = encode the rank-3 maps on the next update launch
   else
@@ -1078,8 +1084,14 @@ ms_solve_backward (ms_ctx *c, double norma)
   MS_CUDA (cudaMemcpyAsync (c->h_flags, c->flags, 8 * sizeof (int), cudaMemcpyDeviceToHost, s));
   MS_TRY (t.finish ());
   int failed = c->h_flags[0] != 0;
+  const int timed_out = c->h_flags[3] != 0;
   if (c->nranks > 1)
     MS_TRY (ms_nccl_agree_flag (c, &failed));
+  if (timed_out)
+    {
+      ms_set_error ("backward sweep: a peer rank never published its part of x (bounded wait expired)");
+      return MS_ERR_CUDA;
+    }
   return failed ? MS_NUMERICAL_FAILURE : MS_OK;
 }
 

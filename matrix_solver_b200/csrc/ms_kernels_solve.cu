@@ -467,49 +467,355 @@ sweep_kernel (const sweep_args sa)
     }
 }
 
+// ============================================================================ backward sweep, any rank count
+// x = R^{-1} D y in ONE launch per rank (compute_x, src/solver.cpp:210-245, without its n gathers).
+// Rank p holds block rows I = p, p + P, ...; its local 64-row chunk lc is global piece
+// gp(lc) = ((lc / q) P + p) q + lc % q  (q = m / 64 pieces per block row).  Chunk lc belongs to CTA lc % G,
+// which keeps that chunk's accumulator  acc = sum_{t > gp} R(chunk, t) x_t  in shared memory.
+// For t = T-1 .. 0:
+//   * the CTA that owns piece t (on the rank that owns its block row) solves R_tt x_t = D y_t - acc_t,
+//     stores x_t into its own x AND into every peer's x (CUDA-IPC mapped pointers: plain stores over
+//     NVLink), fences, and raises ready[t] = epoch in every rank's flag array;
+//   * every CTA of every rank waits for its LOCAL ready[t], reads x_t from its LOCAL x and applies the
+//     64 x 64 blocks R(chunk, t) of the chunks it owns above piece t.
+// The chunk on the critical path (piece t-1) is handled first and everything that does not depend on
+// x_t — its diagonal block and the block R(t-1, t) — is loaded before the CTA waits.
+// No NCCL call and no second launch: at P = 8 the 2 x N_blocks collectives of round 1 (42 ms) are gone.
+// Memory access: a row segment of a block is 512 contiguous bytes; thread (row = tid / 4, g = tid % 4)
+// loads double2 at columns 8 j + 2 g, j = 0..7, so four neighbouring lanes read 64 contiguous bytes and a
+// warp instruction covers 8 rows x 64 B in full sectors; the x_t operands are read as 4 distinct 16-byte
+// words per instruction (broadcast) — no bank conflicts (round 1: 67 % conflict wavefronts, 32 sectors per
+// request).
+// Every wait is bounded (spin_limit clock ticks): a peer that never arrives (crashed rank) makes the
+// kernel give up and report through flags[3] instead of hanging the GPU.
+constexpr int BSWEEP_MAX_PEERS = 16;
+
+struct bsweep_args
+{
+  const double *A;
+  size_t ld, n;
+  const double *y, *d;
+  double *x;       // local x: written by this rank's owners and by the peers' owners
+  int *ready;      // local flags, T ints
+  double *peer_x[BSWEEP_MAX_PEERS];
+  int *peer_ready[BSWEEP_MAX_PEERS];
+  int rank, nranks, q;
+  int epoch, T, LT;
+  double thresh;
+  int *flags;
+  long long spin_limit;
+};
+
+__device__ __forceinline__ bool
+bsweep_wait (const int *flag, int epoch, bool sys, long long limit, bool &gave_up, int *flags)
+{
+  int timed_out = 0;
+  if (threadIdx.x == 0 && !gave_up)
+    {
+      const long long t0 = clock64 ();
+      int v;
+      for (;;)
+        {
+          if (sys)
+            asm volatile ("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          else
+            asm volatile ("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          if (v == epoch)
+            break;
+          if (clock64 () - t0 > limit)
+            {
+              timed_out = 1;
+              flags[3] = 1;
+              break;
+            }
+          __nanosleep (32);
+        }
+    }
+  if (__syncthreads_or (timed_out))
+    gave_up = true;  // a peer never arrived: finish the loop without waiting again; the host reports it
+  return !gave_up;
+}
+
+// 64 x 64 block R(rows lr0.., cols c0..c0+hc): thread (row, g) -> t[2j], t[2j+1] = columns 8j + 2g, +1
+__device__ __forceinline__ void
+bsweep_block_load (const bsweep_args &sa, size_t lr0, size_t c0, int hc, double (&t)[16])
+{
+  const int row = threadIdx.x >> 2, g = threadIdx.x & 3;
+  const double *rp = sa.A + (lr0 + row) * sa.ld + c0 + 2 * g;
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    {
+      const int col = 8 * j + 2 * g;
+      double2 v = make_double2 (0.0, 0.0);
+      if (col + 1 < hc)
+        v = __ldcs (reinterpret_cast<const double2 *> (rp + 8 * j));
+      else if (col < hc)
+        v.x = __ldcs (rp + 8 * j);
+      t[2 * j] = v.x;
+      t[2 * j + 1] = v.y;
+    }
+}
+
+__device__ __forceinline__ void
+bsweep_block_apply (const double (&t)[16], const double *v, double *accs)
+{
+  const int row = threadIdx.x >> 2, g = threadIdx.x & 3;
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    {
+      const double2 xv = *reinterpret_cast<const double2 *> (v + 8 * j + 2 * g);
+      s0 = fma (t[2 * j], xv.x, s0);
+      s1 = fma (t[2 * j + 1], xv.y, s1);
+    }
+  double s = s0 + s1;
+  s += __shfl_xor_sync (0xffffffffu, s, 1);
+  s += __shfl_xor_sync (0xffffffffu, s, 2);
+  if (g == 0)
+    accs[row] += s;
+}
+
+__global__ void __launch_bounds__ (256)
+bsweep_kernel (const bsweep_args sa)
+{
+  __shared__ double Rs[64 * 65];
+  __shared__ __align__ (16) double vs[64];
+  __shared__ double accs[SWEEP_MAX_SLOTS][64];
+  const int G = gridDim.x, me = blockIdx.x, T = sa.T, P = sa.nranks, q = sa.q;
+  const bool sys = P > 1;
+  bool gave_up = false;
+  for (int e = threadIdx.x; e < SWEEP_MAX_SLOTS * 64; e += 256)
+    (&accs[0][0])[e] = 0.0;
+  __syncthreads ();
+
+  auto piece_h = [&] (int t) { return (int)min ((size_t)64, sa.n - (size_t)t * 64); };
+  auto owner_of = [&] (int t) { return (t / q) % P; };
+  auto lidx_of = [&] (int t) { return ((t / q) / P) * q + t % q; };  // local chunk of an OWNED piece
+  // local chunks whose global piece is < t
+  auto lcut = [&] (int t) {
+    const int I = t / q;
+    if (I % P == sa.rank)
+      return (I / P) * q + t % q;
+    return (I / P + (I % P > sa.rank ? 1 : 0)) * q;
+  };
+
+  auto load_diag = [&] (int t) {
+    const int h = piece_h (t);
+    const size_t r0 = (size_t)t * 64, lr0 = (size_t)lidx_of (t) * 64;
+    double r[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++)
+      {
+        const int e = threadIdx.x + 256 * u, i = e >> 6, j = e & 63;
+        r[u] = (i < h && j < h && j >= i) ? sa.A[(lr0 + i) * sa.ld + r0 + j] : 0.0;
+      }
+#pragma unroll
+    for (int u = 0; u < 16; u++)
+      {
+        const int e = threadIdx.x + 256 * u, i = e >> 6, j = e & 63;
+        Rs[i * 65 + j] = r[u];
+      }
+  };
+
+  // this CTA owns piece t and its accumulator is complete: solve, store x_t everywhere, raise the flags
+  auto solve_and_publish = [&] (int t, bool diag_loaded) {
+    const int h = piece_h (t);
+    const size_t r0 = (size_t)t * 64;
+    if (!diag_loaded)
+      load_diag (t);
+    if (threadIdx.x < 64)
+      {
+        double rhs = 0.0;
+        if (threadIdx.x < h)
+          rhs = sa.d[r0 + threadIdx.x] * sa.y[r0 + threadIdx.x] - accs[lidx_of (t) / G][threadIdx.x];
+        vs[threadIdx.x] = rhs;
+      }
+    __syncthreads ();
+    if (threadIdx.x < 32)
+      warp_tri_solve<false> (Rs, vs, h, sa.thresh, sa.flags);
+    __syncthreads ();
+    // x_t: own copy by threads 0..63, one peer per further group of 64 threads
+    for (int e = threadIdx.x; e < 64 * P; e += 256)
+      {
+        const int dst = e >> 6, i = e & 63;
+        if (i < h)
+          {
+            double *xp = dst == sa.rank ? sa.x : sa.peer_x[dst];
+            xp[r0 + i] = vs[i];
+          }
+      }
+    if (sys)
+      __threadfence_system ();
+    else
+      __threadfence ();
+    __syncthreads ();
+    if ((int)threadIdx.x < P)
+      {
+        int *fp = ((int)threadIdx.x == sa.rank ? sa.ready : sa.peer_ready[threadIdx.x]) + t;
+        if (sys)
+          asm volatile ("st.release.sys.global.s32 [%0], %1;" ::"l"(fp), "r"(sa.epoch) : "memory");
+        else
+          asm volatile ("st.release.gpu.global.s32 [%0], %1;" ::"l"(fp), "r"(sa.epoch) : "memory");
+      }
+  };
+
+  bool solved_ahead = false;  // the piece of this iteration was already solved in the previous one
+  for (int t = T - 1; t >= 0; t--)
+    {
+      const int h = piece_h (t);
+      const size_t r0 = (size_t)t * 64;
+      const int tn = t - 1;
+      const bool own_next = tn >= 0 && owner_of (tn) == sa.rank && lidx_of (tn) % G == me;
+      const bool mine = owner_of (t) == sa.rank && lidx_of (t) % G == me;
+      // this CTA is on the critical path of piece tn; with a single CTA per rank both pieces can be its
+      // own, and then piece t needs the shared triangle first
+      const bool ahead = own_next && !(mine && !solved_ahead);
+      double pre[16];
+      if (ahead)
+        {
+          load_diag (tn);
+          bsweep_block_load (sa, (size_t)lidx_of (tn) * 64, r0, h, pre);
+        }
+      if (mine)
+        {
+          if (!solved_ahead)
+            solve_and_publish (t, false);  // vs = x_t afterwards
+        }
+      else
+        {
+          bsweep_wait (sa.ready + t, sa.epoch, sys, sa.spin_limit, gave_up, sa.flags);
+          if (threadIdx.x < 64)
+            vs[threadIdx.x] = threadIdx.x < h ? __ldcg (sa.x + r0 + threadIdx.x) : 0.0;
+          __syncthreads ();
+        }
+      solved_ahead = false;
+      int lc = lcut (t) - 1;            // last local chunk above piece t ...
+      if (lc >= 0)
+        lc -= ((lc - me) % G + G) % G;  // ... that this CTA owns
+      if (ahead)
+        {
+          // neighbour piece first: finish its accumulator, solve it, publish; then catch up
+          bsweep_block_apply (pre, vs, accs[lidx_of (tn) / G]);
+          double vkeep = 0.0, vnext = 0.0;
+          if (threadIdx.x < 64)
+            vkeep = vs[threadIdx.x];
+          __syncthreads ();  // accumulator of tn complete, vs saved
+          solve_and_publish (tn, true);
+          solved_ahead = true;
+          if (threadIdx.x < 64)
+            {
+              vnext = vs[threadIdx.x];
+              vs[threadIdx.x] = vkeep;
+            }
+          __syncthreads ();
+          for (lc -= G; lc >= 0; lc -= G)
+            {
+              double tt[16];
+              bsweep_block_load (sa, (size_t)lc * 64, r0, h, tt);
+              bsweep_block_apply (tt, vs, accs[lc / G]);
+            }
+          __syncthreads ();  // everybody is done with x_t in vs
+          if (threadIdx.x < 64)
+            vs[threadIdx.x] = vnext;
+        }
+      else
+        for (; lc >= 0; lc -= G)
+          {
+            double tt[16];
+            bsweep_block_load (sa, (size_t)lc * 64, r0, h, tt);
+            bsweep_block_apply (tt, vs, accs[lc / G]);
+          }
+      __syncthreads ();  // accumulators and vs settled before the next piece rewrites them
+    }
+}
+
 // returns MS_OK and sets *done = 1 when the single-launch sweep ran, *done = 0 when the caller has to
-// fall back to the per-piece launches (several ranks, m % 64 != 0, or too many chunks per CTA)
+// fall back to the per-piece launches (m % 64 != 0, too many chunks per CTA; forward: several ranks —
+// there the forward solve normally rides along with the factorisation; backward with several ranks:
+// peer memory not mapped)
+double *ms_p2p_peer_x (const ms_ctx *c, int r);
+int *ms_p2p_peer_sweep_ready (const ms_ctx *c, int r);
+
 int
 ms_k_sweep (ms_ctx *c, bool forward, double thresh, cudaStream_t s, int *done)
 {
   *done = 0;
-  if (c->nranks != 1 || c->m % MS_SUB != 0 || c->no_sweep)
+  if (c->m % MS_SUB != 0 || c->no_sweep)
     return MS_OK;
   const int T = (int)((c->n + 63) / 64);
-  static int max_per_sm = -1;
-  if (max_per_sm < 0)
+  static int max_fwd = -1, max_bwd = -1;
+  if (max_fwd < 0)
     {
       int a = 0, b = 0;
       MS_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&a, sweep_kernel<true>, 256, 0));
-      MS_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b, sweep_kernel<false>, 256, 0));
-      max_per_sm = std::max (1, std::min (std::min (a, b), 4));
+      MS_CUDA (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&b, bsweep_kernel, 256, 0));
+      max_fwd = std::max (1, std::min (a, 4));
+      max_bwd = std::max (1, std::min (b, 4));
     }
-  int G = std::min (T, max_per_sm * c->sm_count);
-  if ((T + G - 1) / G > SWEEP_MAX_SLOTS)
-    return MS_OK;
-  if (!c->sweep_ready)
+  if (forward)
     {
-      MS_CUDA (cudaMalloc (&c->sweep_ready, ((size_t)T + 8) * sizeof (int)));
-      MS_CUDA (cudaMemsetAsync (c->sweep_ready, 0, ((size_t)T + 8) * sizeof (int), s));
+      if (c->nranks != 1)
+        return MS_OK;
+      int G = std::min (T, max_fwd * c->sm_count);
+      if ((T + G - 1) / G > SWEEP_MAX_SLOTS)
+        return MS_OK;
+      sweep_args sa;
+      sa.A = c->A;
+      sa.ld = c->ld;
+      sa.n = c->n;
+      sa.b = c->vec[MS_VEC_B];
+      sa.d = c->vec[MS_VEC_D];
+      sa.out = c->vec[MS_VEC_Y];
+      sa.ready = c->sweep_ready;
+      sa.epoch = ++c->sweep_epoch;
+      sa.T = T;
+      sa.thresh = thresh;
+      sa.flags = c->flags;
+      void *args[] = {(void *)&sa};
+      MS_CUDA (cudaLaunchCooperativeKernel ((void *)sweep_kernel<true>, dim3 (G), dim3 (256), args, 0, s));
+      LAUNCH_COUNT (c);
+      *done = 1;
+      return MS_OK;
     }
-  sweep_args sa;
+  // backward: every rank launches its own kernel; the kernels talk through peer memory
+  if (c->nranks > BSWEEP_MAX_PEERS)
+    return MS_OK;
+  bsweep_args sa = {};
+  for (int r = 0; r < c->nranks; r++)
+    if (r != c->rank)
+      {
+        sa.peer_x[r] = ms_p2p_peer_x (c, r);
+        sa.peer_ready[r] = ms_p2p_peer_sweep_ready (c, r);
+        if (!sa.peer_x[r] || !sa.peer_ready[r])
+          return MS_OK;  // transport off on ALL ranks (they agreed at ms_create): per-piece path
+      }
+  const int LT = (int)(c->rows_local / 64);  // m % 64 == 0: only the last global piece can be short ...
+  const int LT_all = (int)((c->rows_local + 63) / 64);  // ... and it is a chunk of its owner
+  (void)LT;
+  int G = std::max (1, std::min (LT_all, max_bwd * c->sm_count));
+  if ((LT_all + G - 1) / G > SWEEP_MAX_SLOTS)
+    return MS_OK;  // rank-independent in practice (n / (64 P) chunks against 4 x 148 CTAs x 24 slots)
   sa.A = c->A;
   sa.ld = c->ld;
   sa.n = c->n;
-  sa.b = forward ? c->vec[MS_VEC_B] : c->vec[MS_VEC_Y];
+  sa.y = c->vec[MS_VEC_Y];
   sa.d = c->vec[MS_VEC_D];
-  sa.out = forward ? c->vec[MS_VEC_Y] : c->vec[MS_VEC_X];
+  sa.x = c->vec[MS_VEC_X];
   sa.ready = c->sweep_ready;
+  sa.rank = c->rank;
+  sa.nranks = c->nranks;
+  sa.q = (int)(c->m / MS_SUB);
   sa.epoch = ++c->sweep_epoch;
   sa.T = T;
+  sa.LT = LT_all;
   sa.thresh = thresh;
   sa.flags = c->flags;
-  void *args[] = {(void *)&sa};
-  if (forward)
-    MS_CUDA (cudaLaunchCooperativeKernel ((void *)sweep_kernel<true>, dim3 (G), dim3 (256), args, 0, s));
-  else
-    MS_CUDA (cudaLaunchCooperativeKernel ((void *)sweep_kernel<false>, dim3 (G), dim3 (256), args, 0, s));
-  LAUNCH_COUNT (c);
+  sa.spin_limit = 6000000000ll;  // ~3 s of SM clock: far beyond any healthy sweep
   *done = 1;
+  if (LT_all == 0)
+    return MS_OK;  // more ranks than block rows: nothing to solve here, the peers still deliver x
+  void *args[] = {(void *)&sa};
+  MS_CUDA (cudaLaunchCooperativeKernel ((void *)bsweep_kernel, dim3 (G), dim3 (256), args, 0, s));
+  LAUNCH_COUNT (c);
   return MS_OK;
 }

@@ -564,10 +564,16 @@ ms_probe_dmma_peak (int device, double *tflops)
   cudaEvent_t e0, e1;
   MS_CUDA (cudaEventCreate (&e0));
   MS_CUDA (cudaEventCreate (&e1));
+  // The clocks ramp up over the first tens of milliseconds of load (a probe of five 4 ms launches was seen
+  // to return 29.7 TFLOP/s = 0.8 x 37.1 on a GPU that had just been idle): warm up for ~150 ms, then take
+  // the best of 20 launches.
   dmma_probe_kernel<<<blocks, 256>>> (d, 64);
   MS_CUDA (cudaDeviceSynchronize ());
+  for (int rep = 0; rep < 36; rep++)
+    dmma_probe_kernel<<<blocks, 256>>> (d, iters);
+  MS_CUDA (cudaDeviceSynchronize ());
   double best = 0;
-  for (int rep = 0; rep < 5; rep++)
+  for (int rep = 0; rep < 20; rep++)
     {
       MS_CUDA (cudaEventRecord (e0));
       dmma_probe_kernel<<<blocks, 256>>> (d, iters);

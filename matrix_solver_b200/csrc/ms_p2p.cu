@@ -6,8 +6,9 @@
 
 namespace
 {
-constexpr int SIG_INTS = 256;      // [0..2] ready per panel buffer, [16 + r] credit from rank r
+constexpr int SIG_INTS = 256;      // [I % 16] ready flag of panel I, [16 + r] credit from rank r
 constexpr int SIG_READY = 0;
+constexpr int SIG_READY_SLOTS = 16;
 constexpr int SIG_CREDIT = 16;
 constexpr int STAGE_SLOTS = 64;
 
@@ -19,6 +20,8 @@ struct p2p_state
   std::vector<int> stage_next;              // one ring of STAGE_SLOTS per stream (index = peer, P = misc)
   std::vector<double *> peer_pb[MS_NPB];    // peers' panel buffers (IPC mapped), [rank]
   std::vector<double *> peer_d;             // peers' d vectors
+  std::vector<double *> peer_x;             // peers' x vectors (backward sweep: owners store x_t into them)
+  std::vector<int *> peer_sweep;            // peers' sweep flags
   std::vector<int *> peer_sig;
   std::vector<void *> opened;
   std::vector<cudaStream_t> s_peer;         // one copy stream per peer: transfers to different
@@ -86,7 +89,7 @@ ms_p2p_enabled (const ms_ctx *c)
 
 namespace
 {
-constexpr int NH = MS_NPB + 2;  // IPC handles per rank: [PB0 PB1 PB2 d sig]
+constexpr int NH = MS_NPB + 4;  // IPC handles per rank: [PB0 PB1 PB2 d sig x sweep_ready]
 
 // everything that involves only this rank: flag words, streams, and the handles the peers will open
 int
@@ -111,6 +114,8 @@ local_setup (ms_ctx *c, p2p_state *p, std::vector<char> &mine)
     ptrs[b] = c->PB[b];
   ptrs[MS_NPB] = c->vec[MS_VEC_D];
   ptrs[MS_NPB + 1] = p->sig;
+  ptrs[MS_NPB + 2] = c->vec[MS_VEC_X];
+  ptrs[MS_NPB + 3] = c->sweep_ready;
   for (int i = 0; i < NH; i++)
     MS_CUDA (cudaIpcGetMemHandle ((cudaIpcMemHandle_t *)(mine.data () + i * hb), ptrs[i]));
   return MS_OK;
@@ -125,6 +130,8 @@ open_peers (ms_ctx *c, p2p_state *p, const std::vector<char> &all)
     p->peer_pb[b].assign (P, nullptr);
   p->peer_d.assign (P, nullptr);
   p->peer_sig.assign (P, nullptr);
+  p->peer_x.assign (P, nullptr);
+  p->peer_sweep.assign (P, nullptr);
   const char *force = getenv ("MS_P2P_FORCE_FAIL");  // test hook: pretend rank <value> cannot map its peers
   if (force && atoi (force) == c->rank)
     {
@@ -151,8 +158,12 @@ open_peers (ms_ctx *c, p2p_state *p, const std::vector<char> &all)
             p->peer_pb[i][r] = (double *)q;
           else if (i == MS_NPB)
             p->peer_d[r] = (double *)q;
-          else
+          else if (i == MS_NPB + 1)
             p->peer_sig[r] = (int *)q;
+          else if (i == MS_NPB + 2)
+            p->peer_x[r] = (double *)q;
+          else
+            p->peer_sweep[r] = (int *)q;
         }
     }
   return MS_OK;
@@ -175,13 +186,24 @@ ms_p2p_init (ms_ctx *c)
   std::vector<char> mine (NH * hb, 0), all ((size_t)P * NH * hb);
   int bad = local_setup (c, p, mine) != MS_OK;
 
-  char *dbuf = nullptr;
-  MS_CUDA (cudaMalloc (&dbuf, all.size ()));
-  MS_CUDA (cudaMemcpy (dbuf + (size_t)c->rank * NH * hb, mine.data (), mine.size (), cudaMemcpyHostToDevice));
-  MS_TRY (ms_nccl_allgather_bytes (c, dbuf + (size_t)c->rank * NH * hb, dbuf, NH * hb, c->s_main));
-  MS_CUDA (cudaStreamSynchronize (c->s_main));
-  MS_CUDA (cudaMemcpy (all.data (), dbuf, all.size (), cudaMemcpyDeviceToHost));
-  MS_CUDA (cudaFree (dbuf));
+  // every rank walks the SAME collectives from here on, whatever failed locally: failures only set
+  // `bad`, and the agreement below sends everybody to the NCCL transport together.  The exchange buffer
+  // is the context's device staging area (allocated long ago), so nothing here can fail half way.
+  char *dbuf = (char *)c->d_stage;
+  if (all.size () > 2 * c->stage_doubles * sizeof (double))
+    bad = 1;
+  if (!bad && cudaMemcpy (dbuf + (size_t)c->rank * NH * hb, mine.data (), mine.size (), cudaMemcpyHostToDevice) != cudaSuccess)
+    {
+      ms_set_error ("ms_p2p_init: staging the IPC handles failed: %s", cudaGetErrorString (cudaGetLastError ()));
+      bad = 1;
+    }
+  int coll = ms_nccl_allgather_bytes (c, dbuf + (size_t)c->rank * NH * hb, dbuf, NH * hb, c->s_main);
+  if (coll == MS_OK && cudaStreamSynchronize (c->s_main) != cudaSuccess)
+    coll = MS_ERR_CUDA;
+  if (coll == MS_OK && !bad && cudaMemcpy (all.data (), dbuf, all.size (), cudaMemcpyDeviceToHost) != cudaSuccess)
+    bad = 1;
+  if (coll != MS_OK)
+    bad = 1;  // a failed collective is fatal for NCCL too, but the agreement is still attempted by all
 
   if (!bad)
     bad = open_peers (c, p, all) != MS_OK;
@@ -257,11 +279,10 @@ ms_p2p_begin_factor (ms_ctx *c)
 //              d_I into its own, then posts credit[rank] = epoch + I + 1 into the owner's memory
 //   owner    : before it writes the same buffer again (panel I+3, factored or pulled) it waits for all
 //              credits of panel I
-// ready[b] is shared by panels I, I+3, I+6 ... which may have different owners, so two GPUs write the
-// same word without a common order; the values only ever grow in program order, and the write for panel
-// I+3 cannot be issued before its owner has consumed panels I+1 and I+2 (whole factorisation steps
-// after the 4-byte copy for panel I was enqueued on an otherwise idle stream).  If that margin ever
-// becomes a concern, index the flags by I % 16 instead of by buffer.
+// The ready flag of panel I is word I % 16: with the rank counts of one box (2, 4, 8, 16 all divide 16)
+// every word has exactly one writer, the owner of block rows I, I+16, ..., whose posts are ordered on one
+// stream and only ever grow — a flag can never move backwards (round 1 shared one word per panel buffer
+// between different owners and relied on a timing margin).
 int
 ms_p2p_send_panel (ms_ctx *c, size_t I, int pb, cudaEvent_t factored)
 {
@@ -274,7 +295,7 @@ ms_p2p_send_panel (ms_ctx *c, size_t I, int pb, cudaEvent_t factored)
         continue;
       cudaStream_t s = p->s_peer[r];
       MS_CUDA (cudaStreamWaitEvent (s, factored, 0));
-      MS_TRY (post_value (p, r, p->peer_sig[r] + SIG_READY + pb, p->epoch + (unsigned)I + 1, s));
+      MS_TRY (post_value (p, r, p->peer_sig[r] + SIG_READY + (int)(I % SIG_READY_SLOTS), p->epoch + (unsigned)I + 1, s));
     }
   return MS_OK;
 }
@@ -283,7 +304,7 @@ int
 ms_p2p_wait_panel (ms_ctx *c, size_t I, int pb, int owner, cudaStream_t s)
 {
   p2p_state *p = st (c);
-  MS_TRY (wait_value (p, p->sig + SIG_READY + pb, p->epoch + (unsigned)I + 1, s));
+  MS_TRY (wait_value (p, p->sig + SIG_READY + (int)(I % SIG_READY_SLOTS), p->epoch + (unsigned)I + 1, s));
   const bool has_trailing = (I + 1) * c->m < c->n;
   const size_t chunk0 = (I * c->m) / MS_CHUNK;
   const size_t off = chunk0 * c->hpb * MS_CHUNK;
@@ -318,4 +339,17 @@ ms_p2p_release_panel (ms_ctx *c, size_t I, cudaEvent_t freed)
   (void)I;
   (void)freed;
   return MS_OK;  // credits are posted by the pull itself
+}
+
+// backward sweep over peer memory (ms_kernels_solve.cu): rank r's x vector and sweep flags as seen from here
+double *
+ms_p2p_peer_x (const ms_ctx *c, int r)
+{
+  return ms_p2p_enabled (c) ? st (c)->peer_x[r] : nullptr;
+}
+
+int *
+ms_p2p_peer_sweep_ready (const ms_ctx *c, int r)
+{
+  return ms_p2p_enabled (c) ? st (c)->peer_sweep[r] : nullptr;
 }

@@ -23,3 +23,6 @@ int ms_p2p_wait_panel (ms_ctx *c, size_t I, int pb, int owner, cudaStream_t s);
 int ms_p2p_release_panel (ms_ctx *c, size_t I, cudaEvent_t freed);
 void ms_p2p_begin_factor (ms_ctx *c);
 int ms_p2p_end_factor (ms_ctx *c);
+// peer views used by the single-launch backward sweep (null when the transport is off)
+double *ms_p2p_peer_x (const ms_ctx *c, int r);
+int *ms_p2p_peer_sweep_ready (const ms_ctx *c, int r);
