@@ -105,6 +105,11 @@ int ms_download_packed (ms_ctx *ctx, double *body);
  * nranks > 1 (every rank calls, every rank receives) */
 int ms_get_row (ms_ctx *ctx, size_t i, double *buf);
 int ms_get_col (ms_ctx *ctx, size_t j, double *buf);
+/* a window of the stored matrix, rows [row0, row0+nrows) x columns [col0, col0+ncols) -> buf (row-major):
+ * what print_mat_beauty (src/matrix_op.cpp:443-505) needs for its two corners, as strided copies;
+ * entries left of a row's diagonal block are whatever the factorisation left there (never printed).
+ * Collective when nranks > 1. */
+int ms_get_block (ms_ctx *ctx, size_t row0, size_t nrows, size_t col0, size_t ncols, double *buf);
 
 /* ---- right-hand side and norm (src/init.cpp:492-531 init_b_get_norm) -------- */
 int ms_b_and_norm (ms_ctx *ctx, double *norm);

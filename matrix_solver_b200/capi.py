@@ -67,6 +67,7 @@ def load():
         "ms_download_packed": (ci, [vp, vp]),
         "ms_get_row": (ci, [vp, sz, dp]),
         "ms_get_col": (ci, [vp, sz, dp]),
+        "ms_get_block": (ci, [vp, sz, sz, sz, sz, dp]),
         "ms_b_and_norm": (ci, [vp, C.POINTER(cd)]),
         "ms_factor": (ci, [vp, cd, C.POINTER(cd)]),
         "ms_solve_forward": (ci, [vp, cd]),
@@ -96,7 +97,7 @@ def load():
 EXPORTED = [
     "ms_last_error", "ms_device_count", "ms_get_unique_id", "ms_create", "ms_destroy",
     "ms_set_option", "ms_get_stats", "ms_sync", "ms_init_formula", "ms_upload_rows",
-    "ms_download_rows", "ms_host_alloc", "ms_host_free", "ms_upload_packed", "ms_download_packed", "ms_get_row", "ms_get_col", "ms_b_and_norm",
+    "ms_download_rows", "ms_host_alloc", "ms_host_free", "ms_upload_packed", "ms_download_packed", "ms_get_row", "ms_get_col", "ms_get_block", "ms_b_and_norm",
     "ms_factor", "ms_solve_forward", "ms_solve_backward", "ms_residual", "ms_set_vec",
     "ms_get_vec", "ms_block_diag_factor", "ms_block_upper_inverse", "ms_block_panel",
     "ms_block_trsm_panel", "ms_block_update", "ms_block_update_diag", "ms_norm2", "ms_error_vs_planted",
@@ -199,6 +200,11 @@ class Solver:
     def get_row(self, i):
         buf = np.zeros(self.n)
         _check(self.L.ms_get_row(self.h, i, _p(buf)))
+        return buf
+
+    def get_block(self, row0, nrows, col0, ncols):
+        buf = np.zeros((nrows, ncols))
+        _check(self.L.ms_get_block(self.h, row0, nrows, col0, ncols, _p(buf)))
         return buf
 
     def get_col(self, j):

@@ -607,6 +607,46 @@ ms_get_row (ms_ctx *c, size_t i, double *buf)
   return MS_OK;
 }
 
+// A rectangular window of the stored matrix for the printing path (print_mat_beauty,
+// src/matrix_op.cpp:443-505, shows two corners of at most 7 x 7 entries): rows [row0, row0 + nrows),
+// columns [col0, col0 + ncols) -> buf (row-major, nrows x ncols).  One strided copy per block row the
+// window touches instead of one whole-row gather + transfer per printed row; with several ranks the
+// owners' pieces are summed into every rank's copy (the others contribute zeros) before the one D2H.
+extern "C" int
+ms_get_block (ms_ctx *c, size_t row0, size_t nrows, size_t col0, size_t ncols, double *buf)
+{
+  MS_CHECK_ARG (c && buf && nrows >= 1 && ncols >= 1 && row0 + nrows <= c->n && col0 + ncols <= c->n, "bad window");
+  MS_CHECK_ARG (nrows * ncols <= c->stage_doubles, "window larger than the staging buffer");
+  MS_CUDA (cudaSetDevice (c->device));
+  cudaStream_t s = c->s_main;
+  double *stage = c->d_stage;
+  const size_t bytes = nrows * ncols * sizeof (double);
+  if (c->nranks > 1)
+    MS_CUDA (cudaMemsetAsync (stage, 0, bytes, s));
+  for (size_t I = row0 / c->m; I < c->nblocks && I * c->m < row0 + nrows; I++)
+    {
+      if (c->owner_of_block (I) != c->rank)
+        continue;
+      const size_t g0 = std::max (I * c->m, row0);
+      const size_t g1 = std::min (I * c->m + c->block_rows (I), row0 + nrows);
+      const double *src = c->row_ptr (g0) + col0;
+      if (c->nranks == 1)
+        MS_CUDA (cudaMemcpy2DAsync (buf + (g0 - row0) * ncols, ncols * 8, src, c->ld * 8, ncols * 8, g1 - g0,
+                                    cudaMemcpyDeviceToHost, s));
+      else
+        MS_CUDA (cudaMemcpy2DAsync (stage + (g0 - row0) * ncols, ncols * 8, src, c->ld * 8, ncols * 8, g1 - g0,
+                                    cudaMemcpyDeviceToDevice, s));
+    }
+  if (c->nranks > 1)
+    {
+      MS_TRY (ms_nccl_allreduce_sum (c, stage, nrows * ncols, s));
+      MS_CUDA (cudaMemcpyAsync (buf, stage, bytes, cudaMemcpyDeviceToHost, s));
+    }
+  MS_CUDA (cudaStreamSynchronize (s));
+  c->stats.d2h_bytes += (long long)bytes;
+  return MS_OK;
+}
+
 extern "C" int
 ms_get_col (ms_ctx *c, size_t j, double *buf)
 {

@@ -241,6 +241,259 @@ diag_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *
 #endif
 }
 
+// ---------------------------------------------------------------------------- K1, strip schedule (h <= 64)
+// diag_kernel above pays one 256-thread barrier and a shared-memory round trip per pivot: ~870 cycles per
+// pivot, 39 us per 64 x 64 piece — the longest link of the panel chain (profiles/README.md).  The chain of
+// truly dependent operations per pivot is only sqrt -> multiply -> divide -> shuffle -> multiply, multiply,
+// subtract.  Here the pivots go in strips of 8 rows:
+//   pivot warp (warp 0) : keeps the strip in registers (lane = columns lane and lane + 32) and factors it
+//                         with shuffles only — no barrier and no shared memory on the dependent chain;
+//   update warps (1-7)  : S1  apply the previous strip's 8 pivots to the rows of the CURRENT strip (the only
+//                             thing the pivot warp waits for: ~2 elements per thread), then `bar.arrive 1`;
+//                         S2  apply them to all rows below the current strip while the pivot warp factors;
+//                             `bar.sync 2` waits for the pivot warp's strip.
+// Two named barriers per strip, both of the arrive / sync kind, so neither side waits for work it does not
+// need.  Every entry still receives its subtractions in ascending pivot order, each product and difference
+// rounded on its own (the _rn intrinsics keep nvcc from contracting them): results are bit-identical to
+// diag_kernel and to the reference (tests/test_gpu_parity.py::test_diag_factor_and_inverse_bit_exact runs
+// through this kernel for w <= 64).
+__device__ __forceinline__ void
+named_bar_sync (int id, int count)
+{
+  asm volatile ("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void
+named_bar_arrive (int id, int count)
+{
+  asm volatile ("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// factor the 8-row strip held in c[u][half] (rows i0 + u, columns lane + 32 * half); LO = the strip still
+// has columns < 32 (i0 < 32), otherwise only the upper half of the columns exists
+template <bool LO>
+__device__ __forceinline__ void
+strip_factor (double (&c)[8][2], int i0, int h, int lane, double thresh, double *rdiag, double *dd, int *flags)
+{
+  const int j0 = lane, j1 = lane + 32;
+#pragma unroll
+  for (int t = 0; t < 8; t++)
+    {
+      const int row = i0 + t;
+      if (row < h)
+        {
+          const double s = __shfl_sync (0xffffffffu, LO ? c[t][0] : c[t][1], row & 31);
+          const double di = s > 0 ? 1.0 : -1.0;
+          const double rii = __dsqrt_rn (fabs (s));
+          const double den = __dmul_rn (rii, di);
+          if (lane == (row & 31))
+            {
+              rdiag[row] = rii;
+              dd[row] = di;
+              if (fabs (rii) < thresh)
+                flags[0] = 1;
+            }
+          if (LO && j0 > row)
+            c[t][0] = __ddiv_rn (c[t][0], den);
+          if (j1 > row)
+            c[t][1] = __ddiv_rn (c[t][1], den);
+#pragma unroll
+          for (int u = t + 1; u < 8; u++)
+            {
+              // r(row, k), k = i0 + u, lives in the lane that owns column k
+              const double rk = __shfl_sync (0xffffffffu, LO ? c[t][0] : c[t][1], (i0 + u) & 31);
+              if (LO)
+                c[u][0] = __dsub_rn (c[u][0], __dmul_rn (__dmul_rn (rk, c[t][0]), di));
+              c[u][1] = __dsub_rn (c[u][1], __dmul_rn (__dmul_rn (rk, c[t][1]), di));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__ (256)
+diag_strip_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *__restrict__ d_out,
+                   double *__restrict__ wt_out, int wt_h, double *__restrict__ inv_out, int want_inverse,
+                   const double *__restrict__ pre_diag, size_t pre_ld, int pre_count, int *flags)
+{
+  constexpr int NB = 8, S = MS_SUB + 1;
+  extern __shared__ double smd[];
+  double *a = smd;                       // [64][65], rows >= h and columns >= h are zero
+  double *v = a + (size_t)MS_SUB * S;    // inverse (only when wanted)
+  double *rdiag = v + (size_t)MS_SUB * S;
+  double *dd = rdiag + MS_SUB;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  // the reference's pre-update pivot test (src/solver.cpp:117) for the whole block row
+  for (int i = tid; i < pre_count; i += 256)
+    if (fabs (pre_diag[(size_t)i * pre_ld + i]) < thresh)
+      flags[0] = 1;
+
+  for (int i = ty; i < MS_SUB; i += 16)
+    for (int j = tx; j < MS_SUB; j += 16)
+      {
+        a[i * S + j] = (i < h && j < h && j >= i) ? blk[(size_t)i * ld + j] : 0.0;
+        if (want_inverse)
+          v[i * S + j] = 0.0;
+      }
+  __syncthreads ();
+
+  const int nstrips = (h + NB - 1) / NB;
+  for (int b = 0; b < nstrips; b++)
+    {
+      const int i0 = NB * b;
+      if (warp == 0)
+        {
+          // ---- pivot warp: wait for S1 (strip rows carry every pivot < i0), factor out of registers
+          if (b > 0)
+            named_bar_sync (1, 256);
+          double c[NB][2];
+#pragma unroll
+          for (int u = 0; u < NB; u++)
+            {
+              c[u][0] = a[(i0 + u) * S + lane];
+              c[u][1] = a[(i0 + u) * S + lane + 32];
+            }
+          if (i0 < 32)
+            strip_factor<true> (c, i0, h, lane, thresh, rdiag, dd, flags);
+          else
+            strip_factor<false> (c, i0, h, lane, thresh, rdiag, dd, flags);
+#pragma unroll
+          for (int u = 0; u < NB; u++)
+            {
+              const int row = i0 + u;
+              if (lane > row)
+                a[row * S + lane] = c[u][0];
+              if (lane + 32 > row)
+                a[row * S + lane + 32] = c[u][1];
+            }
+          named_bar_arrive (2, 256);
+        }
+      else
+        {
+          const int t2 = tid - 32;  // 0 .. 223
+          if (b > 0)
+            {
+              // ---- S1: previous strip's pivots (rows i0-8 .. i0-1, final) into the rows of this strip
+              for (int e = t2; e < NB * MS_SUB; e += 224)
+                {
+                  const int k = i0 + (e >> 6), j = e & 63;
+                  if (j >= k && j < h && k < h)
+                    {
+                      double cv = a[k * S + j];
+#pragma unroll
+                      for (int t = 0; t < NB; t++)
+                        {
+                          const int i = i0 - NB + t;
+                          cv = __dsub_rn (cv, __dmul_rn (__dmul_rn (a[i * S + k], a[i * S + j]), dd[i]));
+                        }
+                      a[k * S + j] = cv;
+                    }
+                }
+              named_bar_arrive (1, 256);
+              // ---- S2: the same pivots into every row below this strip (14 x 16 thread grid; at most 48 rows
+              // and columns remain once i0 + 8 >= 16)
+              const int base = i0 + NB;
+              if (base < h)
+                {
+                  constexpr int NTR = 4, NTC = 3;
+                  const int ux = t2 & 15, uy = t2 >> 4;
+                  double c[NTR][NTC];
+#pragma unroll
+                  for (int u = 0; u < NTR; u++)
+#pragma unroll
+                    for (int w = 0; w < NTC; w++)
+                      {
+                        const int k = base + uy + 14 * u, j = base + ux + 16 * w;
+                        c[u][w] = (k < h && j < h && j >= k) ? a[k * S + j] : 0.0;
+                      }
+#pragma unroll
+                  for (int t = 0; t < NB; t++)
+                    {
+                      const int i = i0 - NB + t;
+                      const double di = dd[i];
+                      double rk[NTR], rj[NTC];
+#pragma unroll
+                      for (int u = 0; u < NTR; u++)
+                        {
+                          const int k = base + uy + 14 * u;
+                          rk[u] = k < h ? a[i * S + k] : 0.0;
+                        }
+#pragma unroll
+                      for (int w = 0; w < NTC; w++)
+                        {
+                          const int j = base + ux + 16 * w;
+                          rj[w] = j < h ? a[i * S + j] : 0.0;
+                        }
+#pragma unroll
+                      for (int u = 0; u < NTR; u++)
+#pragma unroll
+                        for (int w = 0; w < NTC; w++)
+                          c[u][w] = __dsub_rn (c[u][w], __dmul_rn (__dmul_rn (rk[u], rj[w]), di));
+                    }
+#pragma unroll
+                  for (int u = 0; u < NTR; u++)
+#pragma unroll
+                    for (int w = 0; w < NTC; w++)
+                      {
+                        const int k = base + uy + 14 * u, j = base + ux + 16 * w;
+                        if (k < h && j < h && j >= k)
+                          a[k * S + j] = c[u][w];
+                      }
+                }
+            }
+          named_bar_sync (2, 256);  // strip b is final in shared memory
+        }
+    }
+  __syncthreads ();
+
+  // ---- K2: inverse, one thread per column, rows bottom-up, k ascending (as in diag_kernel)
+  if (want_inverse)
+    {
+      for (int j = tid; j < h; j += 256)
+        {
+          for (int i = j; i >= 0; i--)
+            {
+              double val;
+              if (i == j)
+                val = __ddiv_rn (1.0, rdiag[i]);
+              else
+                {
+                  double sum = 0;
+                  for (int k = i + 1; k <= j; k++)
+                    sum = __dadd_rn (sum, __dmul_rn (a[i * S + k], v[k * S + j]));
+                  val = __ddiv_rn (-sum, rdiag[i]);
+                }
+              v[i * S + j] = val;
+            }
+        }
+      __syncthreads ();
+    }
+
+  // ---- write back: R in place (upper), d, the inverse, and Wt = inverse * D (chunk-major)
+  for (int i = ty; i < h; i += 16)
+    for (int j = tx; j < h; j += 16)
+      {
+        if (j > i)
+          blk[(size_t)i * ld + j] = a[i * S + j];
+        else if (j == i)
+          blk[(size_t)i * ld + j] = rdiag[i];
+        if (inv_out)
+          inv_out[(size_t)i * h + j] = j >= i ? v[i * S + j] : 0.0;
+      }
+  if (d_out)
+    for (int i = tid; i < h; i += 256)
+      d_out[i] = dd[i];
+  if (wt_out)
+    for (int k = ty; k < wt_h; k += 16)
+      for (int i = tx; i < wt_h; i += 16)
+        {
+          double val = (k < h && i < h && i >= k) ? v[k * S + i] * dd[i] : 0.0;
+          wt_out[chunk_major_index (k, i, wt_h)] = val;
+        }
+}
+
 // d_out: h doubles (device), wt_out: chunk-major [MS_SUB/16][MS_SUB][16] or null.  The inverse is
 // computed only when someone consumes it (wt_out / inv_out).  pre_diag/pre_ld/pre_count: diagonal to
 // run the pre-update pivot test on (the whole block row, handed to its first piece).
@@ -260,9 +513,22 @@ ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_ou
     {
       MS_CUDA (cudaFuncSetAttribute (diag_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       MS_CUDA (cudaFuncSetAttribute (diag_kernel<8, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      MS_CUDA (cudaFuncSetAttribute (diag_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       configured = true;
     }
-  if (h <= 64)
+  static int strip = -1;
+  if (strip < 0)
+    {
+      const char *e = getenv ("MS_DIAG_STRIP");
+      strip = e ? atoi (e) : 1;
+    }
+  if (h <= 64 && strip)
+    {
+      const size_t smem64 = (2 * (size_t)MS_SUB * (MS_SUB + 1) + 2 * MS_SUB) * sizeof (double);
+      diag_strip_kernel<<<1, 256, smem64, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse,
+                                               pre_diag, pre_ld, pre_count, c->flags);
+    }
+  else if (h <= 64)
     diag_kernel<5, 4><<<1, 256, smem, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse,
                                            pre_diag, pre_ld, pre_count, c->flags);
   else

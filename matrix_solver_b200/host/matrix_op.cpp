@@ -3,7 +3,8 @@
 //   minus_RTDRu_ofast / _l (:41-99, :224-242)   -> ms_block_update_diag
 //   reverse_upper (:244-285)                    -> ms_block_upper_inverse
 //   DRtA / DRtA_l (:287-368)                    -> ms_block_panel
-//   print_mat_beauty / print_vec (:443-522)     -> same text, rows fetched with gather_row
+//   print_mat_beauty / print_vec (:443-522)     -> same text, the two printed corners fetched as two strided
+//                                                  window copies (ms_get_block)
 //   norma_vec2 / find_error (:524-548)          -> ms_norm2 / ms_error_vs_planted
 #include "matrix_op.h"
 
@@ -70,40 +71,49 @@ void
 print_mat_beauty (int root, size_t n, size_t m, double **&rows_p, size_t len, bool log, int width,
                   int precision)
 {
+  (void)m;
   if (len == -1UL || len > n)
     len = n;
   const bool me = ms_rt_rank () == root;
   const int cell = width + (log ? 1 : 0);
-  std::vector<double> row (n);
   auto put = [&] (double v) { printf (log ? "% *.*e " : "%*.*lf ", width, precision, v); };
   auto blanks = [&] (size_t cells) {
     for (size_t c = 0; c < cells; c++)
       printf ("%*s ", cell, "");
   };
-  for (size_t i = 0; i < len; i++)
-    {
-      gather_row (i, n, m, root, row.data (), rows_p);
-      if (!me)
-        continue;
-      blanks (i);
-      for (size_t j = i; j < len; j++)
-        put (row[j]);
-      printf ("\n");
-    }
+  // the two corners arrive as two strided window copies (ms_get_block), not one gathered row per line
+  ms_ctx *c = ms_rt_ctx (rows_p);
+  if (!c)
+    ms_rt_die ("print_mat_beauty: rows_p was not produced by alloc_rows", -1);
+  std::vector<double> win (len * len);
+  if (len > 0)
+    must (ms_get_block (c, 0, len, 0, len, win.data ()), "ms_get_block");
+  if (me)
+    for (size_t i = 0; i < len; i++)
+      {
+        blanks (i);
+        for (size_t j = i; j < len; j++)
+          put (win[i * len + j]);
+        printf ("\n");
+      }
   const size_t first = n - len > len ? n - len : len;
-  for (size_t i = first; i < n; i++)
+  const size_t tail = n - first;
+  if (tail > 0)
     {
-      gather_row (i, n, m, root, row.data (), rows_p);
-      if (!me)
-        continue;
-      for (int k = 0; k < cell; k++)
-        putchar ('.');
-      putchar (' ');
-      blanks (i - first);
-      for (size_t j = i; j < n; j++)
-        put (row[j]);
-      printf ("\n");
+      win.assign (tail * tail, 0.0);
+      must (ms_get_block (c, first, tail, first, tail, win.data ()), "ms_get_block");
     }
+  if (me)
+    for (size_t i = first; i < n; i++)
+      {
+        for (int k = 0; k < cell; k++)
+          putchar ('.');
+        putchar (' ');
+        blanks (i - first);
+        for (size_t j = i; j < n; j++)
+          put (win[(i - first) * tail + (j - first)]);
+        printf ("\n");
+      }
 }
 
 void
