@@ -91,6 +91,10 @@ int ms_init_formula (ms_ctx *ctx, int kind);
  * pageable sources are staged through the library's pinned buffer first. */
 int ms_upload_rows (ms_ctx *ctx, const double *rows, size_t row0, size_t nrows,
                     size_t ld_host);
+/* the same for page-locked rows without waiting: the DMA is queued and the call returns; `rows` must not be
+ * touched until ms_sync (or a later synchronous call) returns.  Lets a reader parse the next chunk of a
+ * file while the previous one is on its way (host/init.cpp init_mat_file). */
+int ms_upload_rows_async (ms_ctx *ctx, const double *rows, size_t row0, size_t nrows, size_t ld_host);
 /* the reverse: the upper part (j >= i, from the start of each row's diagonal block) of the rows
  * this rank owns inside [row0, row0+nrows) is written into `rows`; other entries are untouched */
 int ms_download_rows (ms_ctx *ctx, double *rows, size_t row0, size_t nrows, size_t ld_host);

@@ -60,6 +60,7 @@ def load():
         "ms_sync": (ci, [vp]),
         "ms_init_formula": (ci, [vp, ci]),
         "ms_upload_rows": (ci, [vp, vp, sz, sz, sz]),
+        "ms_upload_rows_async": (ci, [vp, vp, sz, sz, sz]),
         "ms_download_rows": (ci, [vp, vp, sz, sz, sz]),
         "ms_host_alloc": (ci, [C.POINTER(vp), sz]),
         "ms_host_free": (ci, [vp]),
@@ -96,7 +97,7 @@ def load():
 
 EXPORTED = [
     "ms_last_error", "ms_device_count", "ms_get_unique_id", "ms_create", "ms_destroy",
-    "ms_set_option", "ms_get_stats", "ms_sync", "ms_init_formula", "ms_upload_rows",
+    "ms_set_option", "ms_get_stats", "ms_sync", "ms_init_formula", "ms_upload_rows", "ms_upload_rows_async",
     "ms_download_rows", "ms_host_alloc", "ms_host_free", "ms_upload_packed", "ms_download_packed", "ms_get_row", "ms_get_col", "ms_get_block", "ms_b_and_norm",
     "ms_factor", "ms_solve_forward", "ms_solve_backward", "ms_residual", "ms_set_vec",
     "ms_get_vec", "ms_block_diag_factor", "ms_block_upper_inverse", "ms_block_panel",

@@ -320,6 +320,8 @@ ms_set_option (ms_ctx *c, const char *key, long value)
     c->no_sweep = value == 0;
   else if (!strcmp (key, "fuse_forward"))
     c->fuse_forward = value != 0 && c->aug_cols > 0;
+  else if (!strcmp (key, "tile_band_w"))
+    c->tile_band_w = (int)std::max (0l, value);
   else if (!strcmp (key, "tile_tma3"))
     c->tm3_state = value ? 0 : -1;  // 0 = encode the rank-3 maps on the next update launch
   else
@@ -411,7 +413,7 @@ stage_h2d (ms_ctx *c, int half, const double *src, size_t cnt)
 // layout: only columns >= the start of the block row's diagonal block move (n(n+m)/2 doubles
 // in total instead of n^2).
 static int
-rows_dma (ms_ctx *c, double *rows, size_t row0, size_t nrows, size_t ld_host, bool to_device)
+rows_dma (ms_ctx *c, double *rows, size_t row0, size_t nrows, size_t ld_host, bool to_device, bool wait = true)
 {
   for (size_t I = row0 / c->m; I < c->nblocks && I * c->m < row0 + nrows; I++)
     {
@@ -434,8 +436,23 @@ rows_dma (ms_ctx *c, double *rows, size_t row0, size_t nrows, size_t ld_host, bo
           c->stats.d2h_bytes += (long long)(width * (g1 - g0));
         }
     }
-  MS_CUDA (cudaStreamSynchronize (c->s_main));
+  if (wait)
+    MS_CUDA (cudaStreamSynchronize (c->s_main));
   return MS_OK;
+}
+
+// The same transfer without waiting for it: the copies are queued on the library's stream and the call
+// returns.  `rows` must be page-locked and must stay untouched until ms_sync (or any later synchronous
+// call on this context) has returned — the file reader parses its next chunk into a second buffer meanwhile
+// (parse of chunk k+1 overlapped with the DMA of chunk k).
+extern "C" int
+ms_upload_rows_async (ms_ctx *c, const double *rows, size_t row0, size_t nrows, size_t ld_host)
+{
+  MS_CHECK_ARG (c && rows, "null argument");
+  MS_CHECK_ARG (row0 + nrows <= c->n && ld_host >= c->n, "row range / ld out of bounds");
+  MS_CHECK_ARG (is_pinned_host (rows), "ms_upload_rows_async needs page-locked rows (ms_host_alloc)");
+  MS_CUDA (cudaSetDevice (c->device));
+  return rows_dma (c, const_cast<double *> (rows), row0, nrows, ld_host, true, false);
 }
 
 extern "C" int

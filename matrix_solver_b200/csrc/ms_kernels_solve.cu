@@ -575,7 +575,7 @@ bsweep_block_apply (const double (&t)[16], const double *v, double *accs)
     accs[row] += s;
 }
 
-__global__ void __launch_bounds__ (256)
+__global__ void __launch_bounds__ (256, 2)
 bsweep_kernel (const bsweep_args sa)
 {
   __shared__ double Rs[64 * 65];
@@ -670,12 +670,22 @@ bsweep_kernel (const bsweep_args sa)
       // this CTA is on the critical path of piece tn; with a single CTA per rank both pieces can be its
       // own, and then piece t needs the shared triangle first
       const bool ahead = own_next && !(mine && !solved_ahead);
-      double pre[16];
+      int lc = lcut (t) - 1;            // last local chunk above piece t ...
+      if (lc >= 0)
+        lc -= ((lc - me) % G + G) % G;  // ... that this CTA owns (== the chunk of piece tn when `ahead`)
+      // Everything that does not depend on x_t is fetched BEFORE the CTA waits for it: the blocks
+      // R(chunk, t) of its first two chunks (with 4 x 148 chunks per step in flight the HBM latency hides
+      // behind the wait, not behind the 64 FMAs), and for the CTA on the critical path also the triangle
+      // of piece tn.
+      double buf0[16], buf1[16];
+      // (the CTA on the critical path keeps only its critical block across the solve: registers)
+      const int lc0 = lc, lc1 = (!ahead && lc >= G) ? lc - G : -1;
       if (ahead)
-        {
-          load_diag (tn);
-          bsweep_block_load (sa, (size_t)lidx_of (tn) * 64, r0, h, pre);
-        }
+        load_diag (tn);
+      if (lc0 >= 0)
+        bsweep_block_load (sa, (size_t)lc0 * 64, r0, h, buf0);
+      if (lc1 >= 0)
+        bsweep_block_load (sa, (size_t)lc1 * 64, r0, h, buf1);
       if (mine)
         {
           if (!solved_ahead)
@@ -689,13 +699,11 @@ bsweep_kernel (const bsweep_args sa)
           __syncthreads ();
         }
       solved_ahead = false;
-      int lc = lcut (t) - 1;            // last local chunk above piece t ...
-      if (lc >= 0)
-        lc -= ((lc - me) % G + G) % G;  // ... that this CTA owns
+      if (lc0 >= 0)
+        bsweep_block_apply (buf0, vs, accs[lc0 / G]);
       if (ahead)
         {
-          // neighbour piece first: finish its accumulator, solve it, publish; then catch up
-          bsweep_block_apply (pre, vs, accs[lidx_of (tn) / G]);
+          // neighbour piece first: its accumulator is complete now — solve it, publish, then catch up
           double vkeep = 0.0, vnext = 0.0;
           if (threadIdx.x < 64)
             vkeep = vs[threadIdx.x];
@@ -708,23 +716,25 @@ bsweep_kernel (const bsweep_args sa)
               vs[threadIdx.x] = vkeep;
             }
           __syncthreads ();
-          for (lc -= G; lc >= 0; lc -= G)
+          for (lc = lc0 - G; lc >= 0; lc -= G)
             {
-              double tt[16];
-              bsweep_block_load (sa, (size_t)lc * 64, r0, h, tt);
-              bsweep_block_apply (tt, vs, accs[lc / G]);
+              bsweep_block_load (sa, (size_t)lc * 64, r0, h, buf0);
+              bsweep_block_apply (buf0, vs, accs[lc / G]);
             }
           __syncthreads ();  // everybody is done with x_t in vs
           if (threadIdx.x < 64)
             vs[threadIdx.x] = vnext;
         }
       else
-        for (; lc >= 0; lc -= G)
-          {
-            double tt[16];
-            bsweep_block_load (sa, (size_t)lc * 64, r0, h, tt);
-            bsweep_block_apply (tt, vs, accs[lc / G]);
-          }
+        {
+          if (lc1 >= 0)
+            bsweep_block_apply (buf1, vs, accs[lc1 / G]);
+          for (lc = lc1 - G; lc >= 0; lc -= G)
+            {
+              bsweep_block_load (sa, (size_t)lc * 64, r0, h, buf0);
+              bsweep_block_apply (buf0, vs, accs[lc / G]);
+            }
+        }
       __syncthreads ();  // accumulators and vs settled before the next piece rewrites them
     }
 }

@@ -27,12 +27,15 @@
 // neighbouring columns 2p, 2p+1 of k-row 8g+2q+e, which under the 128B swizzle sit in 16-byte
 // slot (p ^ (2q+e)) of that row: the 8 lanes of every quarter warp hit 8 distinct slots.
 #include <algorithm>
+#include <vector>
 
 #include "ms_common.cuh"
 
 #define LAUNCH_COUNT(c) ((c)->stats.kernel_launches++)
 
 // ============================================================================ DMMA tile kernel
+constexpr int TILE_MAX_BANDS = 64;
+
 struct tile_args
 {
   // TMA coordinates of 16-column chunk `ch` at k-row kk:  x = x0 + ch*xs,  y = y0 + ch*ys + kk
@@ -57,6 +60,13 @@ struct tile_args
   size_t n;                 // columns >= n are never written
   size_t n_rows;            // rows >= n_rows do not exist (n < n_rows + 1 only without the augmented column)
   int tiles_per_cta;        // consecutive tiles one CTA walks before it retires
+  // L2-friendly rasterisation (host-built, tile_build_bands): the stored tiles are walked band by band
+  // (band = band_w consecutive column tiles), row tile by row tile inside a band.  Band b starts at tile
+  // band_start[b]; its first band_r1[b] row tiles own the whole band width, row tiles
+  // [band_r1[b], band_r2[b]) start inside the band, later row tiles own nothing of it.
+  int band_w, n_bands;
+  int band_start[TILE_MAX_BANDS + 1];
+  int band_r1[TILE_MAX_BANDS], band_r2[TILE_MAX_BANDS];
 };
 
 constexpr int TILE_A_BYTES = (MS_BM / MS_CHUNK) * MS_KC * MS_CHUNK * 8;  // 8 KB
@@ -65,6 +75,7 @@ constexpr int TILE_STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;            // 24 K
 constexpr int TILE_CHUNK_BYTES = MS_KC * MS_CHUNK * 8;                   // 2 KB
 constexpr int TILE_MAX_K = 1024;
 constexpr int TILE_MAX_RT = 2048;  // row tiles per launch (the host splits larger ranges)
+constexpr int TILE_BAND_W = 64;    // column tiles per band: an 8192-column slab of the panel (16 MB at K = 256)
 constexpr int TILE_SMEM_BYTES = MS_STAGES * TILE_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/
                                 + TILE_MAX_K * 4 + (TILE_MAX_RT + 2) * 4;
 
@@ -86,14 +97,28 @@ tile_first_col_tile (const tile_args &ta, int mode, size_t g)
 }
 
 __host__ __device__ __forceinline__ int
-tile_count_in_row (const tile_args &ta, int mode, int rt)
+tile_total_col_tiles (const tile_args &ta)
+{
+  return (int)((ta.n + MS_BN - 1) / MS_BN);
+}
+
+// first column tile a row tile owns, == the number of column tiles when it owns none (row tiles past
+// the last row).  Non-decreasing in rt: the local rows of a launch ascend in global row order.
+__host__ __device__ __forceinline__ int
+tile_first_in_row (const tile_args &ta, int mode, int rt)
 {
   const size_t g = tile_row_global (ta, mode, rt);
+  const int total = tile_total_col_tiles (ta);
   if (g >= ta.n_rows)
-    return 0;
-  const size_t total = (ta.n + MS_BN - 1) / MS_BN;
+    return total;
   const size_t first = tile_first_col_tile (ta, mode, g);
-  return first < total ? (int)(total - first) : 0;
+  return first < (size_t)total ? (int)first : total;
+}
+
+__host__ __device__ __forceinline__ int
+tile_count_in_row (const tile_args &ta, int mode, int rt)
+{
+  return tile_total_col_tiles (ta) - tile_first_in_row (ta, mode, rt);
 }
 
 // Each CTA walks `tiles_per_cta` consecutive entries of the list of stored tiles (same row tile =
@@ -136,24 +161,57 @@ struct tile_pos
   size_t g_row0, ct;
 };
 
-// tile number t of the launch -> (row tile, its global first row, column tile)
+// tile number t of the launch -> (row tile, its global first row, column tile) in the banded order.
+// prefF[rt] = sum of tile_first_in_row over row tiles < rt (shared memory, built in the prologue).
+//
+// Why bands: walked row tile by row tile, every row tile streams the WHOLE panel as its B operand —
+// 134 MB at n = 65536, more than the 126 MB L2 — and ncu measured 53.7 GB of DRAM reads for 16.8 GB of C
+// in the step-0 launch (profiles/r02_ncu_update_bsweep.txt, 2.09 x the algorithmic bytes).  Inside a band
+// the B slab is 64 column tiles (16 MB at K = 256) and stays in L2 while all row tiles pass over it; the
+// A slabs (128 KB per row tile) are re-read once per band.
 template <int MODE>
 __device__ __forceinline__ tile_pos
-tile_decode (const tile_args &ta, const int *pref, int n_rt, int t)
+tile_decode (const tile_args &ta, const int *prefF, int n_rt, int t)
 {
-  int lo = 0, hi = n_rt - 1;
-  while (lo < hi)
+  int b = 0, bh = ta.n_bands - 1;
+  while (b < bh)
     {
-      const int mid = (lo + hi + 1) >> 1;
-      if (pref[mid] <= t)
-        lo = mid;
+      const int mid = (b + bh + 1) >> 1;
+      if (ta.band_start[mid] <= t)
+        b = mid;
       else
-        hi = mid - 1;
+        bh = mid - 1;
     }
+  const int lo_ct = b * ta.band_w;
+  const int hi_ct = min (lo_ct + ta.band_w, tile_total_col_tiles (ta));
+  const int wfull = hi_ct - lo_ct;
+  const int r1 = ta.band_r1[b], r2 = ta.band_r2[b];
+  int o = t - ta.band_start[b];
   tile_pos tp;
-  tp.rt = lo;
-  tp.g_row0 = tile_row_global (ta, MODE, lo);
-  tp.ct = tile_first_col_tile (ta, MODE, tp.g_row0) + (size_t)(t - pref[lo]);
+  if (o < r1 * wfull)
+    {
+      tp.rt = o / wfull;
+      tp.ct = (size_t)(lo_ct + (o - tp.rt * wfull));
+    }
+  else
+    {
+      // row tiles [r1, r2) start inside the band: cum(rt) = tiles of [r1, rt) = (rt - r1) hi - (prefF[rt] - prefF[r1])
+      o -= r1 * wfull;
+      int lo = r1, hi = r2 - 1;
+      while (lo < hi)
+        {
+          const int mid = (lo + hi + 1) >> 1;
+          if ((mid - r1) * hi_ct - (prefF[mid] - prefF[r1]) <= o)
+            lo = mid;
+          else
+            hi = mid - 1;
+        }
+      tp.rt = lo;
+      const int first = prefF[lo + 1] - prefF[lo];
+      tp.ct = (size_t)(first + (o - ((lo - r1) * hi_ct - (prefF[lo] - prefF[r1]))));
+    }
+  tp.g_row0 = tile_row_global (ta, MODE, tp.rt);
+  (void)n_rt;
   return tp;
 }
 
@@ -394,7 +452,7 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t *full_bar = (uint64_t *)(smem + MS_STAGES * TILE_STAGE_BYTES);
   uint64_t *empty_bar = full_bar + MS_STAGES;
   uint32_t *sgn = (uint32_t *)(empty_bar + MS_STAGES + 8);
-  int *pref = (int *)(sgn + TILE_MAX_K);  // pref[rt] = tiles in row tiles < rt
+  int *pref = (int *)(sgn + TILE_MAX_K);  // pref[rt] = sum of the first column tiles of row tiles < rt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = ta.K / MS_KC;  // multiple of 4 (the host checks K % 64 == 0)
@@ -417,7 +475,7 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
       my_neg |= neg;
     }
   for (int rt = threadIdx.x; rt < n_rt; rt += TILE_THREADS)
-    pref[rt + 1] = tile_count_in_row (ta, MODE, rt);
+    pref[rt + 1] = tile_first_in_row (ta, MODE, rt);
   const bool any_neg = __syncthreads_or (my_neg) != 0;
   if (warp == 0)
     {
@@ -446,7 +504,7 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
         pref[0] = 0;
     }
   __syncthreads ();
-  const int total_tiles = pref[n_rt];
+  const int total_tiles = ta.band_start[ta.n_bands];
 
   const int p = lane >> 2, q = lane & 3;
   const int wm = warp >> 2;  // rows  wm*32
@@ -689,13 +747,35 @@ ms_tile_setup (ms_ctx *c)
   return MS_OK;
 }
 
+// fills the band table of `ta` and returns the number of stored tiles of the launch
 static int
-tile_total (const tile_args &ta, int mode)
+tile_build_bands (const ms_ctx *c, tile_args &ta, int mode)
 {
-  long long total = 0;
-  for (int rt = 0; rt < ta.n_row_tiles; rt++)
-    total += tile_count_in_row (ta, mode, rt);
-  return (int)std::min<long long> (total, 0x7fffffff);
+  const int total_ct = tile_total_col_tiles (ta);
+  const int n_rt = ta.n_row_tiles;
+  ta.band_w = std::max (c->tile_band_w > 0 ? c->tile_band_w : TILE_BAND_W, (total_ct + TILE_MAX_BANDS - 1) / TILE_MAX_BANDS);
+  ta.n_bands = std::max (1, (total_ct + ta.band_w - 1) / ta.band_w);
+  std::vector<int> first (n_rt);
+  std::vector<long long> pref (n_rt + 1, 0);
+  for (int rt = 0; rt < n_rt; rt++)
+    {
+      first[rt] = tile_first_in_row (ta, mode, rt);
+      pref[rt + 1] = pref[rt] + first[rt];
+    }
+  long long start = 0;
+  for (int b = 0; b < ta.n_bands; b++)
+    {
+      const int lo = b * ta.band_w, hi = std::min (lo + ta.band_w, total_ct);
+      // first[] is non-decreasing
+      const int r1 = (int)(std::upper_bound (first.begin (), first.end (), lo) - first.begin ());
+      const int r2 = (int)(std::lower_bound (first.begin (), first.end (), hi) - first.begin ());
+      ta.band_start[b] = (int)std::min<long long> (start, 0x7fffffff);
+      ta.band_r1[b] = r1;
+      ta.band_r2[b] = r2;
+      start += (long long)r1 * (hi - lo) + (long long)(r2 - r1) * hi - (pref[r2] - pref[r1]);
+    }
+  ta.band_start[ta.n_bands] = (int)std::min<long long> (start, 0x7fffffff);
+  return ta.band_start[ta.n_bands];
 }
 
 // Tiles per CTA.  Running CTAs are never preempted: the high-priority panel chain (diag, TRSM, the
@@ -746,7 +826,7 @@ ms_k_tile_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_en
       ta.n_row_tiles = (int)((lr_end - lr + MS_BM - 1) / MS_BM);
       ta.n = c->ncols;
       ta.n_rows = c->n;
-      int total = tile_total (ta, MS_MODE_UPDATE);
+      int total = tile_build_bands (c, ta, MS_MODE_UPDATE);
       if (total == 0)
         continue;
       ta.tiles_per_cta = tiles_per_cta_for (c, total);
@@ -793,7 +873,7 @@ ms_k_tile_panel (ms_ctx *c, int pb, const ms_piece &pc, size_t I, cudaStream_t s
   ta.col_lo_panel = col_lo;
   ta.n = c->ncols;
   ta.n_rows = c->n;
-  int total = tile_total (ta, MS_MODE_PANEL);
+  int total = tile_build_bands (c, ta, MS_MODE_PANEL);
   if (total == 0)
     return MS_OK;
   ta.tiles_per_cta = tiles_per_cta_for (c, total);

@@ -156,19 +156,18 @@ init_mat_file (double **rows_p, size_t n, size_t m, const char *filename)
       printf ("cant open %s\n", filename);
       return 0;
     }
-  // rows are parsed into page-locked memory so that ms_upload_rows can DMA them straight into place
+  // Rows are parsed into page-locked memory and DMA-ed straight into place.  Two chunks alternate: while
+  // the copy engine moves chunk k (ms_upload_rows_async), the host parses chunk k + 1 into the other
+  // buffer; the ms_sync before the next upload waits for a transfer that has had a whole parse to finish.
   const size_t chunk = std::max<size_t> (1, ((size_t)1 << 22) / n);
-  void *pinned = nullptr;
+  void *pinned[2] = {nullptr, nullptr};
   std::vector<double> pageable;
-  double *rows;
-  if (ms_host_alloc (&pinned, chunk * n * sizeof (double)) == 0)
-    rows = (double *)pinned;
-  else
-    {
-      pageable.resize (chunk * n);
-      rows = pageable.data ();
-    }
+  const bool two = ms_host_alloc (&pinned[0], chunk * n * sizeof (double)) == 0
+                   && ms_host_alloc (&pinned[1], chunk * n * sizeof (double)) == 0;
+  if (!two)
+    pageable.resize (chunk * n);
   bool ok = true;
+  int cur = 0;
   for (size_t i0 = 0; i0 < n && ok; i0 += chunk)
     {
       const size_t want = std::min (chunk, n - i0);
@@ -179,16 +178,25 @@ init_mat_file (double **rows_p, size_t n, size_t m, const char *filename)
       size_t got;
       if (owned)
         {
+          double *rows = two ? (double *)pinned[cur] : pageable.data ();
           got = reader.read_rows (rows, want);
-          if (got > 0)
+          if (got > 0 && two)
+            {
+              must (ms_sync (c), "ms_sync");  // the previous chunk's DMA (it ran while this one was parsed)
+              must (ms_upload_rows_async (c, rows, i0, got, n), "ms_upload_rows_async");
+              cur ^= 1;
+            }
+          else if (got > 0)
             must (ms_upload_rows (c, rows, i0, got, n), "ms_upload_rows");
         }
       else
         got = reader.skip_rows (want);
       ok = got == want;
     }
-  if (pinned)
-    ms_host_free (pinned);
+  must (ms_sync (c), "ms_sync");
+  for (void *p : pinned)
+    if (p)
+      ms_host_free (p);
   if (!ok)
     printf ("unexpected eof of %s\n", filename);
   return ok;

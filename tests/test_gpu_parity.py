@@ -301,6 +301,11 @@ def test_tile_kernel_rank3_and_2d_tma_loads_agree(ms, n, m):
     base = gpu_pipeline(ms, n, m)
     alt = gpu_pipeline(ms, n, m, options=(("tile_tma3", 0),))
     assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
+    # the order in which the stored tiles are walked (bands of "tile_band_w" column tiles; 64 by default,
+    # i.e. a single band at these n) must not change a bit either: 1 and 3 give many bands here
+    for bw in (1, 3):
+        alt = gpu_pipeline(ms, n, m, options=(("tile_band_w", bw),))
+        assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
     rng = np.random.default_rng(5)
     sign = np.where(np.arange(n) % 7 == 3, -1.0, 1.0)
     L = np.tril(rng.standard_normal((n, n)) * 0.05, -1) + np.eye(n)
@@ -396,6 +401,21 @@ def test_cpp_mirror_entry_points(ms, ora, tmp_path):
     want = np.triu(np.fromfunction(lambda i, j: n - np.maximum(i, j), (n, n)))
     want[3, 5] += 0.5
     assert np.array_equal(a, want)
+
+
+def test_get_block_windows_match_gathered_rows(ms):
+    """ms_get_block (the printing path's two corner windows) against ms_get_row."""
+    n, m = 200, 64
+    with ms.Solver(n, m) as s:
+        s.init_formula(0)
+        full = s.get_upper()
+        for row0, nrows, col0, ncols in [(0, 7, 0, 7), (193, 7, 193, 7), (60, 10, 60, 10), (0, 200, 0, 200),
+                                         (63, 2, 100, 50), (128, 72, 128, 72)]:
+            win = s.get_block(row0, nrows, col0, ncols)
+            for i in range(nrows):
+                for j in range(ncols):
+                    if col0 + j >= row0 + i:
+                        assert win[i, j] == full[row0 + i, col0 + j]
 
 
 def test_hilbert_generator(ms):

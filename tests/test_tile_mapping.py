@@ -194,41 +194,85 @@ def test_rank3_tensor_map_addresses_the_chunk_major_buffer():
                 assert swizzled_byte(dy, x) // 128 == dy
 
 
-# ---- the tile list of one update launch (tile_row_global / tile_first_col_tile / tile_count_in_row and
-# ---- the walk in tile_dmma_kernel: prefix scan over row tiles, binary search, T tiles per CTA)
+# ---- the tile list of one update launch (tile_row_global / tile_first_in_row / tile_build_bands and
+# ---- the walk in tile_dmma_kernel: band table, prefix scan over row tiles, two binary searches, T tiles per CTA)
 def _tile_row_global(lrow_begin, m, rank, nranks, rt):
     l = lrow_begin + rt * BM
     lb = l // m
     return (lb * nranks + rank) * m + (l - lb * m)
 
 
-def _launch_tiles(n, m, rank, nranks, lrow_begin, lrow_end, tiles_per_cta):
+def _launch_tiles(n, m, rank, nranks, lrow_begin, lrow_end, tiles_per_cta, ncols=None, band_w_min=64, max_bands=64):
+    """tile_build_bands (host) + tile_decode (device) of csrc/ms_kernels_tile.cu: the stored tiles are
+    walked band by band (band = band_w column tiles), row tile by row tile inside a band."""
+    ncols = n if ncols is None else ncols                # n + 1 with the augmented column
     n_rt = (lrow_end - lrow_begin + BM - 1) // BM
-    total_ct = (n + BN - 1) // BN
-    counts = []
+    total_ct = (ncols + BN - 1) // BN
+    first = []
     for rt in range(n_rt):
         g = _tile_row_global(lrow_begin, m, rank, nranks, rt)
-        first = g // BN
-        counts.append(max(0, total_ct - first) if g < n else 0)
-    pref = [0]
-    for c in counts:
-        pref.append(pref[-1] + c)
-    total = pref[-1]
+        first.append(min(g // BN, total_ct) if g < n else total_ct)
+    assert first == sorted(first)                        # the band table relies on it
+    prefF = [0]
+    for f in first:
+        prefF.append(prefF[-1] + f)
+    band_w = max(band_w_min, (total_ct + max_bands - 1) // max_bands)
+    n_bands = max(1, (total_ct + band_w - 1) // band_w)
+    start, r1s, r2s = [0], [], []
+    for b in range(n_bands):
+        lo, hi = b * band_w, min((b + 1) * band_w, total_ct)
+        r1 = sum(1 for f in first if f <= lo)
+        r2 = sum(1 for f in first if f < hi)
+        r1s.append(r1)
+        r2s.append(r2)
+        start.append(start[-1] + r1 * (hi - lo) + (r2 - r1) * hi - (prefF[r2] - prefF[r1]))
+    total = start[-1]
+    assert total == sum(total_ct - f for f in first)
     tiles = []
     n_cta = (total + tiles_per_cta - 1) // tiles_per_cta
     for cta in range(n_cta):
         for t in range(cta * tiles_per_cta, min(total, (cta + 1) * tiles_per_cta)):
-            lo, hi = 0, n_rt - 1
-            while lo < hi:                               # the kernel's binary search
-                mid = (lo + hi + 1) >> 1
-                if pref[mid] <= t:
-                    lo = mid
+            b, bh = 0, n_bands - 1                       # the kernel's two binary searches
+            while b < bh:
+                mid = (b + bh + 1) >> 1
+                if start[mid] <= t:
+                    b = mid
                 else:
-                    hi = mid - 1
-            g_row0 = _tile_row_global(lrow_begin, m, rank, nranks, lo)
-            ct = g_row0 // BN + (t - pref[lo])
-            tiles.append((lo, g_row0, ct))
+                    bh = mid - 1
+            lo_ct, hi_ct = b * band_w, min((b + 1) * band_w, total_ct)
+            wfull, r1, r2 = hi_ct - lo_ct, r1s[b], r2s[b]
+            o = t - start[b]
+            if o < r1 * wfull:
+                rt = o // wfull
+                ct = lo_ct + (o - rt * wfull)
+            else:
+                o -= r1 * wfull
+                lo, hi = r1, r2 - 1
+                while lo < hi:
+                    mid = (lo + hi + 1) >> 1
+                    if (mid - r1) * hi_ct - (prefF[mid] - prefF[r1]) <= o:
+                        lo = mid
+                    else:
+                        hi = mid - 1
+                rt = lo
+                ct = (prefF[lo + 1] - prefF[lo]) + (o - ((lo - r1) * hi_ct - (prefF[lo] - prefF[r1])))
+            assert lo_ct <= ct < hi_ct and ct >= first[rt]
+            tiles.append((rt, _tile_row_global(lrow_begin, m, rank, nranks, rt), ct))
     return tiles, total
+
+
+def test_banded_walk_keeps_neighbouring_tiles_on_one_panel_slab():
+    """The point of the bands: the tiles in flight at any time (~1200 consecutive entries of the list) read
+    at most one band's worth of panel columns as their B operand plus a few row tiles' A slabs."""
+    n, m = 65536, 256
+    tiles, total = _launch_tiles(n, m, 0, 1, 768, n, 4, ncols=n + 1)
+    assert total == sum((n + 1 + BN - 1) // BN - (g // BN) for g in range(768, n, BM))
+    window = 1184
+    for s0 in range(0, total - window, 50021):
+        cts = {ct for _, _, ct in tiles[s0:s0 + window]}
+        rts = {rt for rt, _, _ in tiles[s0:s0 + window]}
+        assert max(cts) - min(cts) < 2 * 64           # at most two neighbouring bands
+        assert len(rts) <= window // 16 + 2
 
 
 def test_update_launch_covers_the_stored_trapezoid_exactly_once():
@@ -246,8 +290,8 @@ def test_update_launch_covers_the_stored_trapezoid_exactly_once():
                 lrow_begin = (later[0] // nranks) * m
                 rows_local = sum(min(m, n - J * m) for J in mine)
                 lrow_end = rows_local
-                for T in (1, 4):
-                    tiles, total = _launch_tiles(n, m, rank, nranks, lrow_begin, lrow_end, T)
+                for T, bw in ((1, 64), (4, 2), (4, 1), (3, 3)):   # small band widths: several bands at these n
+                    tiles, total = _launch_tiles(n, m, rank, nranks, lrow_begin, lrow_end, T, band_w_min=bw)
                     assert len(tiles) == total and len(set(tiles)) == total
                     written = {}
                     for rt, g_row0, ct in tiles:
