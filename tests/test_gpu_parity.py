@@ -418,6 +418,33 @@ def test_get_block_windows_match_gathered_rows(ms):
                         assert win[i, j] == full[row0 + i, col0 + j]
 
 
+def test_large_raw_file_through_the_cli(ms, tmp_path):
+    """a > 1 GB matrix file in the raw .f64 format through the drop-in CLI (init_mat_file ->
+    MatrixFileReader -> two alternating pinned chunks -> ms_upload_rows_async), read twice like the reference
+    does (test/test_mat.cpp:89-98 and :149-159).  The file holds the formula matrix, so the planted solution
+    and the formula run of the same size are the known answers."""
+    n, m = 11585, 256
+    path = tmp_path / "big.f64"
+    idx = np.arange(n)
+    with open(path, "wb") as f:
+        for i0 in range(0, n, 1024):
+            rows = n - np.maximum(idx[i0:i0 + 1024, None], idx[None, :])
+            rows.astype(np.float64).tofile(f)
+    assert os.path.getsize(path) == n * n * 8 > 1 << 30
+    exe = os.path.join(ol.ROOT, "matrix_solver_b200", "bin", "test_mat")
+    out_file = subprocess.run([exe, str(n), str(m), str(path)], cwd=tmp_path, capture_output=True, text=True, check=True).stdout
+    out_formula = subprocess.run([exe, str(n), str(m)], cwd=tmp_path, capture_output=True, text=True, check=True).stdout
+    import re
+    pat = re.compile(r"residual = (\S+), er = (\S+), elapsed")
+    rf, ef = (float(v) for v in pat.search(out_file).groups())
+    r0, e0 = (float(v) for v in pat.search(out_formula).groups())
+    assert rf == r0 and ef == e0            # same matrix bits in, same arithmetic: identical results
+    assert ef <= 10 * n * EPS * 1.62 * n * n * np.sqrt(n / 2)
+    # everything but the banner / final line (which carry the file name) is identical text
+    lf, l0 = out_file.strip().split("\n"), out_formula.strip().split("\n")
+    assert lf[1:-1] == l0[1:-1]
+
+
 def test_hilbert_generator(ms):
     """The reference's second generator (test/test_mat.cpp:18-22, hilb = 1/(i+j+1)): device generator
     against numpy, and a solve of the (ill-conditioned) system at a size where it is still SPD in fp64."""
