@@ -80,130 +80,204 @@ ms_k_fill_formula (ms_ctx *c, int kind, cudaStream_t s)
 }
 
 // ----------------------------------------------------------------------------- K9 / K10
-// out_i = sum_k w(k) * Asym(i,k) over the full symmetric row, from the stored upper triangle.
-//   BNORM: w(k) = [k even], plus the absolute row sum (for ||A||_inf)
-//   SYMV : w(k) = x_k
-// Pass 1 (row part, k >= i): one CTA per stored row, coalesced, fixed-order tree reduction.
-// Pass 2 (column part, k < i): thread per column walks a chunk of rows; partials per chunk.
-// Pass 3: fixed-order sum of the partials.  No atomics on the values => deterministic.
-__device__ __forceinline__ double
-block_sum_256 (double v, double *sm)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    v += __shfl_xor_sync (0xffffffffu, v, o);
-  __syncthreads ();
-  if ((threadIdx.x & 31) == 0)
-    sm[threadIdx.x >> 5] = v;
-  __syncthreads ();
-  double t = 0;
-  if (threadIdx.x < 32)
-    {
-      t = threadIdx.x < 8 ? sm[threadIdx.x] : 0.0;
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1)
-        t += __shfl_xor_sync (0xffffffffu, t, o);
-    }
-  return t;  // valid in thread 0
-}
+// out_i = sum_k w(k) * Asym(i,k) over the full symmetric row, from the stored upper triangle, in ONE pass:
+// every stored element A(i,j), j > i, feeds row i (with w_j) and row j (with w_i); the diagonal feeds row i.
+//   BNORM: w(k) = [k even], plus the absolute row sum (for ||A||_inf)    init_b_get_norm, src/init.cpp:492-531
+//   SYMV : w(k) = x_k                                                     find_disrep_vec,  src/init.cpp:533-563
+// (Round 1 read the triangle twice — a row pass and a column pass, 34.4 GB at n = 65536; the reference
+// itself gathers every row and every column, :509-522.)
+//
+// One CTA owns 128 local rows (8 warps x 16 rows) and sweeps their columns from the diagonal to n in chunks
+// of 256: a lane reads double2 at columns 64 k + 2 lane (k = 0..3), so a warp instruction covers 512
+// contiguous bytes of one row.  Row sums stay in registers for the whole sweep (one shuffle reduction per
+// row at the very end); column sums are lane-local over the warp's 16 rows, then the 8 warps are added in
+// a fixed order through shared memory and the CTA writes ONE partial per column and row group.  A second
+// small kernel adds the partials in group order.  No atomics: bit-reproducible.
+constexpr int SYM_ROWS = 128;
+constexpr int SYM_COLS = 256;
 
 template <int MODE>
 __global__ void __launch_bounds__ (256)
-sym_rowpart_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m, size_t rows_local,
-                    int rank, int nranks, const double *__restrict__ x, double *__restrict__ rowS,
-                    double *__restrict__ rowA)
-{
-  __shared__ double sm[8];
-  size_t lr = blockIdx.x;
-  size_t g = global_row_of (lr, m, rank, nranks);
-  const double *row = A + lr * ld;
-  double s = 0, sa = 0;
-  for (size_t j = g + threadIdx.x; j < n; j += 256)
-    {
-      double v = row[j];
-      if (MODE == MS_SYM_BNORM)
-        {
-          if ((j & 1) == 0)
-            s += v;
-          sa += fabs (v);
-        }
-      else
-        s += v * x[j];
-    }
-  double ts = block_sum_256 (s, sm);
-  if (threadIdx.x == 0)
-    rowS[g] = ts;
-  if (MODE == MS_SYM_BNORM)
-    {
-      double ta = block_sum_256 (sa, sm);
-      if (threadIdx.x == 0)
-        rowA[g] = ta;
-    }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__ (256)
-sym_colpart_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m, size_t rows_local,
-                    int rank, int nranks, size_t rows_per_chunk, const double *__restrict__ x,
+sym_onepass_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m, size_t rows_local, int rank,
+                    int nranks, const double *__restrict__ x, double *__restrict__ rowS, double *__restrict__ rowA,
                     double *__restrict__ colS, double *__restrict__ colA)
 {
-  size_t j = (size_t)blockIdx.x * 256 + threadIdx.x;
-  size_t lr0 = (size_t)blockIdx.y * rows_per_chunk;
-  size_t lr1 = lr0 + rows_per_chunk < rows_local ? lr0 + rows_per_chunk : rows_local;
-  double s = 0, sa = 0;
-  if (j < n)
+  constexpr bool NORM = MODE == MS_SYM_BNORM;
+  __shared__ size_t grow[SYM_ROWS];
+  __shared__ double wrow[SYM_ROWS];
+  __shared__ double cpart[8][SYM_COLS];
+  __shared__ double cpartA[NORM ? 8 : 1][SYM_COLS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t lr0 = (size_t)blockIdx.x * SYM_ROWS;
+  if (tid < SYM_ROWS)
     {
-      for (size_t lr = lr0; lr < lr1; lr++)
+      const size_t lr = lr0 + tid;
+      const size_t g = lr < rows_local ? global_row_of (lr, m, rank, nranks) : n;
+      grow[tid] = g < n ? g : n;
+      wrow[tid] = g < n ? (NORM ? ((g & 1) == 0 ? 1.0 : 0.0) : x[g]) : 0.0;
+    }
+  __syncthreads ();
+  const size_t c_first = (grow[0] / SYM_COLS) * SYM_COLS;  // global rows ascend inside a group
+  double racc[16], raccA[NORM ? 16 : 1];
+#pragma unroll
+  for (int r = 0; r < 16; r++)
+    racc[r] = 0.0;
+  if (NORM)
+#pragma unroll
+    for (int r = 0; r < 16; r++)
+      raccA[r] = 0.0;
+
+  for (size_t col0 = c_first; col0 < n; col0 += SYM_COLS)
+    {
+      // weights of this lane's 8 columns for the ROW sums
+      double wc[4][2];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
         {
-          size_t g = global_row_of (lr, m, rank, nranks);
-          if (g >= j)
+          const size_t cj = col0 + 64 * k + 2 * lane;
+          if (NORM)
             {
-              // rows of later blocks can only be larger; within a block rows ascend
-              if (nranks == 1)
-                break;
-              continue;
-            }
-          double v = A[lr * ld + j];
-          if (MODE == MS_SYM_BNORM)
-            {
-              if ((g & 1) == 0)
-                s += v;
-              sa += fabs (v);
+              wc[k][0] = 1.0;  // col0, 64 k and 2 lane are even
+              wc[k][1] = 0.0;
             }
           else
-            s += v * x[g];
+            {
+              wc[k][0] = cj < n ? x[cj] : 0.0;
+              wc[k][1] = cj + 1 < n ? x[cj + 1] : 0.0;
+            }
         }
+      double cacc[4][2], caccA[NORM ? 4 : 1][2];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        {
+          cacc[k][0] = cacc[k][1] = 0.0;
+          if (NORM)
+            caccA[k][0] = caccA[k][1] = 0.0;
+        }
+      // rows go in batches of RB: all loads of a batch are issued before its arithmetic (RB x 4 16-byte
+      // loads in flight per lane; a warp-uniform `continue` per row would serialise the rows' latencies)
+      constexpr int RB = NORM ? 2 : 4;
+#pragma unroll
+      for (int rb = 0; rb < 16; rb += RB)
+        {
+          double2 v[RB][4];
+#pragma unroll
+          for (int rr = 0; rr < RB; rr++)
+            {
+              const int row = warp * 16 + rb + rr;
+              const size_t gi = grow[row];
+              // no such row, or the whole chunk lies left of its diagonal: nothing to read
+              const bool live = gi < n && col0 + SYM_COLS > gi;
+              const double *rp = A + (lr0 + row) * ld + col0 + 2 * lane;
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                v[rr][k] = (live && col0 + 64 * k + 2 * lane < ld) ? __ldcs (reinterpret_cast<const double2 *> (rp + 64 * k))
+                                                                   : make_double2 (0.0, 0.0);
+            }
+#pragma unroll
+          for (int rr = 0; rr < RB; rr++)
+            {
+              const int r = rb + rr;
+              const int row = warp * 16 + r;
+              const size_t gi = grow[row];
+              const double wr = wrow[row];
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                {
+                  const size_t cj = col0 + 64 * k + 2 * lane;
+                  // stored and counted: gi <= column < n  (gi == n for rows that do not exist)
+                  const double a0 = (cj >= gi && cj < n) ? v[rr][k].x : 0.0;
+                  const double a1 = (cj + 1 >= gi && cj + 1 < n) ? v[rr][k].y : 0.0;
+                  racc[r] = fma (a0, wc[k][0], racc[r]);
+                  racc[r] = fma (a1, wc[k][1], racc[r]);
+                  // the mirrored element A(column, gi) exists only strictly above the diagonal
+                  const double b0 = cj > gi ? a0 : 0.0;
+                  const double b1 = cj + 1 > gi ? a1 : 0.0;
+                  cacc[k][0] = fma (b0, wr, cacc[k][0]);
+                  cacc[k][1] = fma (b1, wr, cacc[k][1]);
+                  if (NORM)
+                    {
+                      raccA[r] += fabs (a0) + fabs (a1);
+                      caccA[k][0] += fabs (b0);
+                      caccA[k][1] += fabs (b1);
+                    }
+                }
+            }
+        }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        {
+          cpart[warp][64 * k + 2 * lane] = cacc[k][0];
+          cpart[warp][64 * k + 2 * lane + 1] = cacc[k][1];
+          if (NORM)
+            {
+              cpartA[warp][64 * k + 2 * lane] = caccA[k][0];
+              cpartA[warp][64 * k + 2 * lane + 1] = caccA[k][1];
+            }
+        }
+      __syncthreads ();
+      if (col0 + tid < n)
+        {
+          double s = 0.0, sa = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; w++)
+            {
+              s += cpart[w][tid];
+              if (NORM)
+                sa += cpartA[w][tid];
+            }
+          colS[(size_t)blockIdx.x * n + col0 + tid] = s;
+          if (NORM)
+            colA[(size_t)blockIdx.x * n + col0 + tid] = sa;
+        }
+      __syncthreads ();
     }
-  if (j < n)
+#pragma unroll
+  for (int r = 0; r < 16; r++)
     {
-      colS[(size_t)blockIdx.y * n + j] = s;
-      if (MODE == MS_SYM_BNORM)
-        colA[(size_t)blockIdx.y * n + j] = sa;
+      double s = racc[r], sa = NORM ? raccA[r] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        {
+          s += __shfl_xor_sync (0xffffffffu, s, o);
+          if (NORM)
+            sa += __shfl_xor_sync (0xffffffffu, sa, o);
+        }
+      const size_t gi = grow[warp * 16 + r];
+      if (lane == 0 && gi < n)
+        {
+          rowS[gi] = s;
+          if (NORM)
+            rowA[gi] = sa;
+        }
     }
 }
 
-// total_i = rowS_i + sum_chunks colS[c][i]; BNORM additionally folds the abs sums into a max.
+// total_j = rowS_j + sum over the row groups that reach column j of colS[group][j], in group order;
+// BNORM additionally folds the abs sums.  A group's sweep starts at the 256-column chunk of its first row.
 template <int MODE>
 __global__ void __launch_bounds__ (256)
-sym_finalize_kernel (size_t n, size_t nchunks, const double *__restrict__ rowS,
-                     const double *__restrict__ rowA, const double *__restrict__ colS,
-                     const double *__restrict__ colA, double *__restrict__ out,
+sym_finalize_kernel (size_t n, size_t m, size_t rows_local, int rank, int nranks, size_t ngroups,
+                     const double *__restrict__ rowS, const double *__restrict__ rowA,
+                     const double *__restrict__ colS, const double *__restrict__ colA, double *__restrict__ out,
                      double *__restrict__ outA)
 {
-  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n)
+  size_t j = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= n)
     return;
-  double s = rowS[i];
-  for (size_t c = 0; c < nchunks; c++)
-    s += colS[c * n + i];
-  out[i] = s;
-  if (MODE == MS_SYM_BNORM)
+  double s = rowS[j], a = MODE == MS_SYM_BNORM ? rowA[j] : 0.0;
+  for (size_t g = 0; g < ngroups; g++)
     {
-      double a = rowA[i];
-      for (size_t c = 0; c < nchunks; c++)
-        a += colA[c * n + i];
-      outA[i] = a;
+      const size_t first = global_row_of (g * SYM_ROWS, m, rank, nranks);
+      if ((first / SYM_COLS) * SYM_COLS > j)
+        break;  // first rows ascend with the group index
+      s += colS[g * n + j];
+      if (MODE == MS_SYM_BNORM)
+        a += colA[g * n + j];
     }
+  out[j] = s;
+  if (MODE == MS_SYM_BNORM)
+    outA[j] = a;
 }
 
 __global__ void __launch_bounds__ (1024)
@@ -230,17 +304,15 @@ max_reduce_kernel (const double *__restrict__ v, size_t n, double *__restrict__ 
     }
 }
 
-// scratch layout (doubles): rowS[n] rowA[n] colS[nchunks*n] colA[nchunks*n] outA[n] max[1]
+// scratch layout (doubles): rowS[n] rowA[n] outA[n] max[16] colS[ngroups*n] colA[ngroups*n]
 int
 ms_k_sym_rows (ms_ctx *c, int mode, const double *xvec, double *out, double *norm_out,
                cudaStream_t s)
 {
+  (void)norm_out;
   size_t n = c->n;
-  size_t rpc = 256;
-  while ((c->rows_local + rpc - 1) / rpc > 64)
-    rpc *= 2;
-  size_t nchunks = c->rows_local ? (c->rows_local + rpc - 1) / rpc : 0;
-  size_t need = 3 * n + 2 * nchunks * n + 16;
+  size_t ngroups = (c->rows_local + SYM_ROWS - 1) / SYM_ROWS;
+  size_t need = 3 * n + 16 + 2 * ngroups * n;
   if (need > c->scratch_doubles)
     {
       if (c->scratch)
@@ -249,39 +321,26 @@ ms_k_sym_rows (ms_ctx *c, int mode, const double *xvec, double *out, double *nor
       MS_CUDA (cudaMalloc (&c->scratch, need * sizeof (double)));
       c->scratch_doubles = need;
     }
-  double *rowS = c->scratch, *rowA = rowS + n, *colS = rowA + n, *colA = colS + nchunks * n;
-  double *outA = colA + nchunks * n, *mx = outA + n;
+  double *rowS = c->scratch, *rowA = rowS + n, *outA = rowA + n, *colS = outA + n + 16, *colA = colS + ngroups * n;
   MS_CUDA (cudaMemsetAsync (rowS, 0, 2 * n * sizeof (double), s));
   unsigned gx = (unsigned)((n + 255) / 256);
-  if (c->rows_local)
+  if (ngroups)
     {
       if (mode == MS_SYM_BNORM)
-        {
-          sym_rowpart_kernel<MS_SYM_BNORM><<<(unsigned)c->rows_local, 256, 0, s>>> (
-              c->A, c->ld, n, c->m, c->rows_local, c->rank, c->nranks, xvec, rowS, rowA);
-          sym_colpart_kernel<MS_SYM_BNORM><<<dim3 (gx, (unsigned)nchunks), 256, 0, s>>> (
-              c->A, c->ld, n, c->m, c->rows_local, c->rank, c->nranks, rpc, xvec, colS, colA);
-        }
+        sym_onepass_kernel<MS_SYM_BNORM><<<(unsigned)ngroups, 256, 0, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
+                                                                         c->nranks, xvec, rowS, rowA, colS, colA);
       else
-        {
-          sym_rowpart_kernel<MS_SYM_SYMV><<<(unsigned)c->rows_local, 256, 0, s>>> (
-              c->A, c->ld, n, c->m, c->rows_local, c->rank, c->nranks, xvec, rowS, rowA);
-          sym_colpart_kernel<MS_SYM_SYMV><<<dim3 (gx, (unsigned)nchunks), 256, 0, s>>> (
-              c->A, c->ld, n, c->m, c->rows_local, c->rank, c->nranks, rpc, xvec, colS, colA);
-        }
-      c->stats.kernel_launches += 2;
+        sym_onepass_kernel<MS_SYM_SYMV><<<(unsigned)ngroups, 256, 0, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
+                                                                        c->nranks, xvec, rowS, rowA, colS, colA);
+      LAUNCH_COUNT (c);
     }
   if (mode == MS_SYM_BNORM)
-    sym_finalize_kernel<MS_SYM_BNORM><<<gx, 256, 0, s>>> (n, nchunks, rowS, rowA, colS, colA, out, outA);
+    sym_finalize_kernel<MS_SYM_BNORM><<<gx, 256, 0, s>>> (n, c->m, c->rows_local, c->rank, c->nranks, ngroups, rowS, rowA,
+                                                         colS, colA, out, outA);
   else
-    sym_finalize_kernel<MS_SYM_SYMV><<<gx, 256, 0, s>>> (n, nchunks, rowS, rowA, colS, colA, out, outA);
+    sym_finalize_kernel<MS_SYM_SYMV><<<gx, 256, 0, s>>> (n, c->m, c->rows_local, c->rank, c->nranks, ngroups, rowS, rowA,
+                                                        colS, colA, out, outA);
   LAUNCH_COUNT (c);
-  if (mode == MS_SYM_BNORM && norm_out)
-    {
-      // outA holds this rank's partial abs row sums; the caller all-reduces them when
-      // nranks > 1 and then takes the max via ms_k_max (norm_out == device pointer).
-      (void)mx;
-    }
   MS_CUDA (cudaGetLastError ());
   return MS_OK;
 }
@@ -298,13 +357,9 @@ ms_k_max (ms_ctx *c, const double *v, size_t n, double *d_out, cudaStream_t s)
 double *
 ms_sym_abs_partial (ms_ctx *c)
 {
-  // location of outA inside the scratch area of the last ms_k_sym_rows call
-  size_t n = c->n;
-  size_t rpc = 256;
-  while ((c->rows_local + rpc - 1) / rpc > 64)
-    rpc *= 2;
-  size_t nchunks = c->rows_local ? (c->rows_local + rpc - 1) / rpc : 0;
-  return c->scratch + 2 * n + 2 * nchunks * n;
+  // location of outA (this rank's absolute row sums; n doubles followed by 16 spare ones for the max)
+  // inside the scratch area of the last ms_k_sym_rows call
+  return c->scratch + 2 * c->n;
 }
 
 // ----------------------------------------------------------------------------- norms

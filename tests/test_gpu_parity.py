@@ -423,7 +423,7 @@ def test_large_raw_file_through_the_cli(ms, tmp_path):
     MatrixFileReader -> two alternating pinned chunks -> ms_upload_rows_async), read twice like the reference
     does (test/test_mat.cpp:89-98 and :149-159).  The file holds the formula matrix, so the planted solution
     and the formula run of the same size are the known answers."""
-    n, m = 11585, 256
+    n, m = 11587, 256
     path = tmp_path / "big.f64"
     idx = np.arange(n)
     with open(path, "wb") as f:
