@@ -320,6 +320,8 @@ ms_set_option (ms_ctx *c, const char *key, long value)
     c->no_sweep = value == 0;
   else if (!strcmp (key, "fuse_forward"))
     c->fuse_forward = value != 0 && c->aug_cols > 0;
+  else if (!strcmp (key, "exact_pivots"))
+    c->exact_pivots = value != 0;
   else if (!strcmp (key, "tile_band_w"))
     c->tile_band_w = (int)std::max (0l, value);
   else if (!strcmp (key, "tile_tma3"))
@@ -1195,6 +1197,9 @@ blk_ctx (ms_ctx **out)
       int r = ms_create (&g_blk, 64, 64, dev, 0, 1, nullptr);
       if (r < 0)
         return r;
+      // the block API mirrors the reference's routines one to one: its diagonal-block factor keeps the
+      // reference's sqrt / divide roundings (bit-identical to cholesky_decomp_U), whatever the pipeline does
+      g_blk->exact_pivots = true;
     }
   MS_CUDA (cudaSetDevice (g_blk->device));
   *out = g_blk;

@@ -83,6 +83,7 @@ struct ms_ctx
   size_t ncols = 0;        // columns the factorisation kernels walk: n, or n + 1 when b rides along as
                            // an augmented column (forward solve fused into the factorisation)
   bool fuse_forward = true;
+  bool exact_pivots = false;  // diag kernel with the reference's sqrt / divide roundings ("exact_pivots" option)
   int tile_band_w = 0;     // column tiles per band of the tile walk (0 = default 64; "tile_band_w" option, tests)
   int aug_cols = 1;        // columns reserved right of column n-1 (0 only with MS_FUSE_FORWARD=0 at creation)
   unsigned long long b_version = 1;           // bumped whenever vec[B] is rewritten

@@ -270,35 +270,75 @@ named_bar_arrive (int id, int count)
 }
 
 // factor the 8-row strip held in c[u][half] (rows i0 + u, columns lane + 32 * half); LO = the strip still
-// has columns < 32 (i0 < 32), otherwise only the upper half of the columns exists
-template <bool LO>
+// has columns < 32 (i0 < 32), otherwise only the upper half of the columns exists.
+//
+// What bounds this routine is the pivot warp's INSTRUCTION COUNT: a single warp issues about one instruction
+// every four cycles here (tools/lat_probe.cu and the per-phase stamps of tools/diag_timing.py: 32 register
+// moves cost 130 cycles), so the pivot loop is fully unrolled (static register indices, no rotation, row
+// updates only for the rows that still need them) and the per-pivot arithmetic is kept minimal.
+// FAST: the pivot is taken through y = rsqrt(|s|) (CUDA's rsqrt, 1 ulp): r_ii = |s| y and the row is
+// MULTIPLIED by y d_i — ~15 instructions instead of the ~45 of an IEEE sqrt and two IEEE divides (whose
+// dependent chains, 92 + 125 + 125 cycles, also serialise).  The entries then differ from the reference's
+// sqrt / divide sequence by at most a few ulp — far inside the c n eps cond(A) budget of the factorisation,
+// but not bit-identical any more; !FAST keeps the reference's roundings ("exact_pivots" option, block API).
+constexpr int DIAG_NB = 4;  // pivots per strip: the pivot warp updates (NB - 1 - t) rows per pivot itself
+
+template <bool LO, bool FAST>
 __device__ __forceinline__ void
-strip_factor (double (&c)[8][2], int i0, int h, int lane, double thresh, double *rdiag, double *dd, int *flags)
+strip_factor (double (&c)[DIAG_NB][2], int i0, int h, int lane, double thresh, double *rdiag, double *dd, int *flags)
 {
   const int j0 = lane, j1 = lane + 32;
+  double keep_r = 1.0, keep_d = 1.0;  // lane t keeps pivot t's r_ii and d_i and stores them after the strip
 #pragma unroll
-  for (int t = 0; t < 8; t++)
+  for (int t = 0; t < DIAG_NB; t++)
     {
       const int row = i0 + t;
-      if (row < h)
+      // no `row < h` test here: a GPU does not speculate, and a branch on a kernel argument costs the
+      // dependent chain ~40 cycles per pivot.  Rows >= h are zero padding; their "pivots" produce NaN/inf
+      // that only ever reach other padding rows, and nothing of the padding is written back.
         {
           const double s = __shfl_sync (0xffffffffu, LO ? c[t][0] : c[t][1], row & 31);
           const double di = s > 0 ? 1.0 : -1.0;
-          const double rii = __dsqrt_rn (fabs (s));
-          const double den = __dmul_rn (rii, di);
-          if (lane == (row & 31))
+          double rii, den;
+          if (FAST)
             {
-              rdiag[row] = rii;
-              dd[row] = di;
-              if (fabs (rii) < thresh)
-                flags[0] = 1;
+              const double y = rsqrt (fabs (s));
+              rii = s != 0.0 ? fabs (s) * y : 0.0;  // a zero pivot must fail the threshold test, not turn into NaN
+              den = y * di;                          // the multiplier 1 / (r_ii d_i)
             }
-          if (LO && j0 > row)
-            c[t][0] = __ddiv_rn (c[t][0], den);
-          if (j1 > row)
-            c[t][1] = __ddiv_rn (c[t][1], den);
+          else
+            {
+              rii = __dsqrt_rn (fabs (s));
+              den = __dmul_rn (rii, di);
+            }
+          if (lane == t)
+            {
+              keep_r = rii;
+              keep_d = di;
+            }
+          if (FAST)
+            {
+              if (LO && j0 > row)
+                c[t][0] *= den;
+              if (j1 > row)
+                c[t][1] *= den;
+            }
+          else
+            {
+              // lanes left of the pivot hold 0.0; they divide 1.0 instead so that the quotient the compiler
+              // evaluates for every lane stays on the fast path of the IEEE divide sequence
+              if (LO)
+                {
+                  const double q0 = __ddiv_rn (j0 > row ? c[t][0] : 1.0, den);
+                  if (j0 > row)
+                    c[t][0] = q0;
+                }
+              const double q1 = __ddiv_rn (j1 > row ? c[t][1] : 1.0, den);
+              if (j1 > row)
+                c[t][1] = q1;
+            }
 #pragma unroll
-          for (int u = t + 1; u < 8; u++)
+          for (int u = t + 1; u < DIAG_NB; u++)
             {
               // r(row, k), k = i0 + u, lives in the lane that owns column k
               const double rk = __shfl_sync (0xffffffffu, LO ? c[t][0] : c[t][1], (i0 + u) & 31);
@@ -308,14 +348,27 @@ strip_factor (double (&c)[8][2], int i0, int h, int lane, double thresh, double 
             }
         }
     }
+  if (lane < DIAG_NB && i0 + lane < h)
+    {
+      rdiag[i0 + lane] = keep_r;
+      dd[i0 + lane] = keep_d;
+      if (fabs (keep_r) < thresh)
+        flags[0] = 1;
+    }
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__ (256)
 diag_strip_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, double *__restrict__ d_out,
                    double *__restrict__ wt_out, int wt_h, double *__restrict__ inv_out, int want_inverse,
-                   const double *__restrict__ pre_diag, size_t pre_ld, int pre_count, int *flags)
+                   const double *__restrict__ pre_diag, size_t pre_ld, int pre_count, int *flags,
+                   long long *cyc = nullptr, int solo = 0)
 {
-  constexpr int NB = 8, S = MS_SUB + 1;
+  constexpr int NB = DIAG_NB, S = MS_SUB + 1;
+  // cyc != nullptr (tools/diag_timing.py only): clock64 stamps of the phases, written by thread 0
+  long long tc0 = 0, tc1 = 0, tc2 = 0, acc_wait = 0, acc_fact = 0;
+  if (cyc)
+    tc0 = clock64 ();
   extern __shared__ double smd[];
   double *a = smd;                       // [64][65], rows >= h and columns >= h are zero
   double *v = a + (size_t)MS_SUB * S;    // inverse (only when wanted)
@@ -338,6 +391,8 @@ diag_strip_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, do
           v[i * S + j] = 0.0;
       }
   __syncthreads ();
+  if (cyc)
+    tc1 = clock64 ();
 
   const int nstrips = (h + NB - 1) / NB;
   for (int b = 0; b < nstrips; b++)
@@ -346,8 +401,10 @@ diag_strip_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, do
       if (warp == 0)
         {
           // ---- pivot warp: wait for S1 (strip rows carry every pivot < i0), factor out of registers
-          if (b > 0)
+          long long tw0 = cyc ? clock64 () : 0;
+          if (b > 0 && !solo)
             named_bar_sync (1, 256);
+          long long tw1 = cyc ? clock64 () : 0;
           double c[NB][2];
 #pragma unroll
           for (int u = 0; u < NB; u++)
@@ -356,9 +413,14 @@ diag_strip_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, do
               c[u][1] = a[(i0 + u) * S + lane + 32];
             }
           if (i0 < 32)
-            strip_factor<true> (c, i0, h, lane, thresh, rdiag, dd, flags);
+            strip_factor<true, FAST> (c, i0, h, lane, thresh, rdiag, dd, flags);
           else
-            strip_factor<false> (c, i0, h, lane, thresh, rdiag, dd, flags);
+            strip_factor<false, FAST> (c, i0, h, lane, thresh, rdiag, dd, flags);
+          if (cyc)
+            {
+              acc_wait += tw1 - tw0;
+              acc_fact += clock64 () - tw1;
+            }
 #pragma unroll
           for (int u = 0; u < NB; u++)
             {
@@ -368,14 +430,15 @@ diag_strip_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, do
               if (lane + 32 > row)
                 a[row * S + lane + 32] = c[u][1];
             }
-          named_bar_arrive (2, 256);
+          if (!solo)
+            named_bar_arrive (2, 256);
         }
-      else
+      else if (!solo)
         {
           const int t2 = tid - 32;  // 0 .. 223
           if (b > 0)
             {
-              // ---- S1: previous strip's pivots (rows i0-8 .. i0-1, final) into the rows of this strip
+              // ---- S1: previous strip's pivots (rows i0-NB .. i0-1, final) into the rows of this strip
               for (int e = t2; e < NB * MS_SUB; e += 224)
                 {
                   const int k = i0 + (e >> 6), j = e & 63;
@@ -392,12 +455,12 @@ diag_strip_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, do
                     }
                 }
               named_bar_arrive (1, 256);
-              // ---- S2: the same pivots into every row below this strip (14 x 16 thread grid; at most 48 rows
-              // and columns remain once i0 + 8 >= 16)
+              // ---- S2: the same pivots into every row below this strip (14 x 16 thread grid; at most
+              // 64 - 2 NB rows and columns remain)
               const int base = i0 + NB;
               if (base < h)
                 {
-                  constexpr int NTR = 4, NTC = 3;
+                  constexpr int NTR = (MS_SUB - 2 * NB + 13) / 14, NTC = (MS_SUB - 2 * NB + 15) / 16;
                   const int ux = t2 & 15, uy = t2 >> 4;
                   double c[NTR][NTC];
 #pragma unroll
@@ -447,6 +510,8 @@ diag_strip_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, do
         }
     }
   __syncthreads ();
+  if (cyc)
+    tc2 = clock64 ();
 
   // ---- K2: inverse, one thread per column, rows bottom-up, k ascending (as in diag_kernel)
   if (want_inverse)
@@ -492,6 +557,14 @@ diag_strip_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, do
           double val = (k < h && i < h && i >= k) ? v[k * S + i] * dd[i] : 0.0;
           wt_out[chunk_major_index (k, i, wt_h)] = val;
         }
+  if (cyc && tid == 0)
+    {
+      cyc[0] = tc1 - tc0;          // pre-test + load
+      cyc[1] = tc2 - tc1;          // all strips
+      cyc[2] = clock64 () - tc2;   // inverse (if any) + write back
+      cyc[3] = acc_wait;           // pivot warp: waiting for S1 (bar.sync 1)
+      cyc[4] = acc_fact;           // pivot warp: strip load + factor
+    }
 }
 
 // d_out: h doubles (device), wt_out: chunk-major [MS_SUB/16][MS_SUB][16] or null.  The inverse is
@@ -513,20 +586,24 @@ ms_k_diag (ms_ctx *c, double *blk, size_t ld, int h, double thresh, double *d_ou
     {
       MS_CUDA (cudaFuncSetAttribute (diag_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       MS_CUDA (cudaFuncSetAttribute (diag_kernel<8, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      MS_CUDA (cudaFuncSetAttribute (diag_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      MS_CUDA (cudaFuncSetAttribute (diag_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      MS_CUDA (cudaFuncSetAttribute (diag_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       configured = true;
     }
+  // Full 64-row pieces of the DMMA path take the strip-scheduled kernel with fast pivots; everything else
+  // (short pieces, block sizes that are not multiples of 64 — where the reference's fixtures with their
+  // exactly singular minors live —, the block API, "exact_pivots" = 1) keeps the reference's roundings.
   static int strip = -1;
   if (strip < 0)
     {
       const char *e = getenv ("MS_DIAG_STRIP");
       strip = e ? atoi (e) : 1;
     }
-  if (h <= 64 && strip)
+  if (h == MS_SUB && strip && c->fast && !c->force_generic && !c->exact_pivots)
     {
       const size_t smem64 = (2 * (size_t)MS_SUB * (MS_SUB + 1) + 2 * MS_SUB) * sizeof (double);
-      diag_strip_kernel<<<1, 256, smem64, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse,
-                                               pre_diag, pre_ld, pre_count, c->flags);
+      diag_strip_kernel<true><<<1, 256, smem64, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse,
+                                                     pre_diag, pre_ld, pre_count, c->flags);
     }
   else if (h <= 64)
     diag_kernel<5, 4><<<1, 256, smem, s>>> (blk, ld, h, thresh, d_out, wt_out, MS_SUB, inv_out, want_inverse,
@@ -655,5 +732,67 @@ ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t
   trsm_panel_kernel<<<grid, 128, smem, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H, pb_k0);
   LAUNCH_COUNT (c);
   MS_CUDA (cudaGetLastError ());
+  return MS_OK;
+}
+
+// debug hook (not in the public header): average device time of one diag-kernel launch on a 64 x 64 SPD block
+// (variant 0 = diag_kernel<5,4>, 1 = diag_strip_kernel), in microseconds
+extern "C" int
+ms_debug_time_diag (int variant, int h, int reps, double *us_out, long long *cycles5)
+{
+  // variant 0 = diag_kernel<5,4>, 1 = diag_strip_kernel, 2 = diag_strip_kernel with the update warps and the
+  // barriers switched off (timing of the pivot warp alone; its results are wrong by construction)
+  MS_CHECK_ARG (h >= 1 && h <= 64 && reps >= 1 && us_out, "bad argument");
+  double *blk, *d, *src;
+  int *flags;
+  MS_CUDA (cudaMalloc (&blk, 64 * 64 * 8));
+  MS_CUDA (cudaMalloc (&src, 64 * 64 * 8));
+  MS_CUDA (cudaMalloc (&d, 64 * 8));
+  MS_CUDA (cudaMalloc (&flags, 8 * sizeof (int)));
+  MS_CUDA (cudaMemset (flags, 0, 8 * sizeof (int)));
+  long long *cyc;
+  MS_CUDA (cudaMalloc (&cyc, 64 * sizeof (long long)));
+  MS_CUDA (cudaMemset (cyc, 0, 64 * sizeof (long long)));
+  std::vector<double> a (64 * 64, 0.0);
+  for (int i = 0; i < h; i++)
+    for (int j = i; j < h; j++)
+      a[i * 64 + j] = (double)(h - j) + (i == j ? h : 0);  // min-type SPD matrix plus a diagonal shift
+  MS_CUDA (cudaMemcpy (src, a.data (), 64 * 64 * 8, cudaMemcpyHostToDevice));
+  const size_t smem = (2 * (size_t)MS_SUB * (MS_SUB + 1) + 2 * MS_SUB) * sizeof (double);
+  MS_CUDA (cudaFuncSetAttribute (diag_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  MS_CUDA (cudaFuncSetAttribute (diag_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  MS_CUDA (cudaFuncSetAttribute (diag_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  cudaEvent_t e0, e1;
+  MS_CUDA (cudaEventCreate (&e0));
+  MS_CUDA (cudaEventCreate (&e1));
+  float total = 0;
+  for (int r = 0; r < reps + 2; r++)
+    {
+      MS_CUDA (cudaMemcpy (blk, src, 64 * 64 * 8, cudaMemcpyDeviceToDevice));
+      MS_CUDA (cudaEventRecord (e0));
+      if (variant == 0)
+        diag_kernel<5, 4><<<1, 256, smem>>> (blk, 64, h, 1e-300, d, nullptr, MS_SUB, nullptr, 0, blk, 64, h, flags);
+      else if (variant == 3)
+        diag_strip_kernel<true><<<1, 256, smem>>> (blk, 64, h, 1e-300, d, nullptr, MS_SUB, nullptr, 0, blk, 64, h, flags, cyc, 0);
+      else
+        diag_strip_kernel<false><<<1, 256, smem>>> (blk, 64, h, 1e-300, d, nullptr, MS_SUB, nullptr, 0, blk, 64, h, flags, cyc,
+                                                    variant == 2);
+      MS_CUDA (cudaEventRecord (e1));
+      MS_CUDA (cudaEventSynchronize (e1));
+      float ms;
+      MS_CUDA (cudaEventElapsedTime (&ms, e0, e1));
+      if (r >= 2)
+        total += ms;
+    }
+  *us_out = total / reps * 1e3;
+  if (cycles5)
+    MS_CUDA (cudaMemcpy (cycles5, cyc, 40 * sizeof (long long), cudaMemcpyDeviceToHost));
+  cudaFree (cyc);
+  cudaEventDestroy (e0);
+  cudaEventDestroy (e1);
+  cudaFree (blk);
+  cudaFree (src);
+  cudaFree (d);
+  cudaFree (flags);
   return MS_OK;
 }

@@ -445,6 +445,30 @@ def test_large_raw_file_through_the_cli(ms, tmp_path):
     assert lf[1:-1] == l0[1:-1]
 
 
+@pytest.mark.parametrize("n,m", [(640, 128), (200, 64), (37, 5), (1000, 192)])
+def test_fast_and_exact_pivots_agree(ms, ora, n, m):
+    """Inside the factorisation the diagonal pieces take their pivots through rsqrt and multiply (a few ulp
+    from the reference's sqrt / divide sequence, 3 x shorter dependent chain); "exact_pivots" = 1 selects the
+    reference's roundings.  Both against the oracle within the north star's tolerance, the exact variant
+    against the fast one far inside it, and indefinite input keeps its signs."""
+    o = ora.solve_pipeline(n, m)
+    tol = C_TOL * n * EPS * 1.62 * n * n
+    fast = gpu_pipeline(ms, n, m)
+    exact = gpu_pipeline(ms, n, m, options=(("exact_pivots", 1),))
+    for got in (fast, exact):
+        assert rel(np.triu(got["R"]), np.triu(o["R"])) <= tol and rel(got["x"], o["x"]) <= tol
+        assert got["residual"] <= max(2 * o["residual"], 8 * n * EPS * np.linalg.norm(o["b"]))
+    assert rel(np.triu(fast["R"]), np.triu(exact["R"])) <= 64 * n * EPS
+    rng = np.random.default_rng(21)
+    sign = np.where(np.arange(n) % 4 == 1, -1.0, 1.0)
+    L = np.tril(rng.standard_normal((n, n)) * 0.05, -1) + np.eye(n)
+    indef = L @ np.diag(sign * (1 + rng.random(n))) @ L.T
+    f = gpu_pipeline(ms, n, m, dense=indef)
+    e = gpu_pipeline(ms, n, m, dense=indef, options=(("exact_pivots", 1),))
+    assert np.array_equal(f["d"], sign) and np.array_equal(e["d"], sign)
+    assert rel(np.triu(f["R"]), np.triu(e["R"])) <= 1e-11 and rel(f["x"], e["x"]) <= 1e-9
+
+
 def test_hilbert_generator(ms):
     """The reference's second generator (test/test_mat.cpp:18-22, hilb = 1/(i+j+1)): device generator
     against numpy, and a solve of the (ill-conditioned) system at a size where it is still SPD in fp64."""
