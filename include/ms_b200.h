@@ -73,8 +73,11 @@ int ms_device_count (int *count);
  * (torch.distributed broadcast, a pipe, a file); ignored when nranks == 1.  The id bootstraps an
  * NCCL communicator (reductions of the solves, b/norm, flags); the factored panels themselves move
  * over CUDA-IPC peer memory with copy engines unless MS_P2P=0 (then ncclBroadcast).
- * Options for ms_set_option: "lookahead", "force_generic", "panel_trsm", "single_launch_sweeps",
- * "profile_update" (0/1). */
+ * Options for ms_set_option (0/1 unless noted): "lookahead", "force_generic", "panel_trsm",
+ * "single_launch_sweeps", "profile_update", "fuse_forward" (b rides through ms_factor as an augmented
+ * column; default 1), "exact_pivots" (the reference's sqrt / divide roundings in every diagonal piece;
+ * default 0: full 64-row pieces use rsqrt and a multiply), "tile_tma3", "tile_band_w" (column tiles per
+ * band of the update's tile walk; 0 = default 64). */
 int ms_get_unique_id (void *id128);
 int ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks,
                const void *unique_id);

@@ -126,6 +126,7 @@ ctx_free (ms_ctx *c)
   cudaFree (c->acc);
   cudaFree (c->scratch);
   cudaFree (c->sweep_ready);
+  cudaFree (c->sweep_inv);
   cudaFree (c->flags);
   cudaFree (c->d_stage);
   if (c->h_flags)

@@ -125,6 +125,7 @@ struct ms_ctx
   std::vector<ms_piece> pieces;
   std::vector<size_t> block_first_piece;  // index into pieces, size nblocks+1
 
+  double *sweep_inv = nullptr; // inverses of the local 64 x 64 diagonal pieces (backward sweep), allocated on first use
   int *sweep_ready = nullptr;  // epoch flags of the single-launch sweeps
   int sweep_epoch = 0;
   bool no_sweep = false;       // MS_NO_SWEEP=1: per-piece solve launches

@@ -495,6 +495,7 @@ struct bsweep_args
   const double *A;
   size_t ld, n;
   const double *y, *d;
+  const double *V;  // inverses of this rank's 64 x 64 diagonal pieces, [local chunk][64][64] (bsweep_invert_kernel)
   double *x;       // local x: written by this rank's owners and by the peers' owners
   int *ready;      // local flags, T ints
   double *peer_x[BSWEEP_MAX_PEERS];
@@ -575,11 +576,64 @@ bsweep_block_apply (const double (&t)[16], const double *v, double *accs)
     accs[row] += s;
 }
 
+// The 64 x 64 triangles are inverted once, before the sweep (one CTA per local piece, all in parallel): the
+// per-piece solve on the sweep's critical path is then a matrix-vector product by the whole CTA (~300 cycles)
+// instead of 64 dependent shuffle + FMA steps of one warp (~2500 cycles on each of the n / 64 links of the
+// chain).  Same recurrence as reverse_upper (src/matrix_op.cpp:244-285); the pivot test of compute_x
+// (|R_ii| < EPS * norm, src/solver.cpp:232-236) happens here.
+__global__ void __launch_bounds__ (64)
+bsweep_invert_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m, int rank, int nranks,
+                      double *__restrict__ V, double thresh, int *flags)
+{
+  extern __shared__ double inv_sm[];  // a[64][65] | v[64][65]
+  double *a = inv_sm, *v = inv_sm + 64 * 65;
+  const size_t lr0 = (size_t)blockIdx.x * 64;
+  const size_t lb = lr0 / m;
+  const size_t g0 = (lb * (size_t)nranks + (size_t)rank) * m + (lr0 - lb * m);
+  const int h = g0 < n ? (int)min ((size_t)64, n - g0) : 0;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 64 * 64; e += 64)
+    {
+      const int i = e >> 6, j = e & 63;
+      a[i * 65 + j] = (i < h && j < h && j >= i) ? A[(lr0 + i) * ld + g0 + j] : 0.0;
+      v[i * 65 + j] = 0.0;
+    }
+  __syncthreads ();
+  if (tid < h)
+    {
+      const int j = tid;
+      if (fabs (a[j * 65 + j]) < thresh)
+        flags[0] = 1;
+      for (int i = j; i >= 0; i--)
+        {
+          double val;
+          if (i == j)
+            val = 1.0 / a[i * 65 + i];
+          else
+            {
+              double sum = 0;
+              for (int k = i + 1; k <= j; k++)
+                sum = fma (a[i * 65 + k], v[k * 65 + j], sum);
+              val = -sum / a[i * 65 + i];
+            }
+          v[i * 65 + j] = val;
+        }
+    }
+  __syncthreads ();
+  double *out = V + (size_t)blockIdx.x * 64 * 64;
+  for (int e = tid; e < 64 * 64; e += 64)
+    out[e] = v[(e >> 6) * 65 + (e & 63)];
+}
+
+constexpr int BS_RS = 68;  // row stride of the inverse in shared memory: 4 (mod 16) keeps the product's loads at the
+                           // unavoidable two wavefronts per request
+
 __global__ void __launch_bounds__ (256, 2)
 bsweep_kernel (const bsweep_args sa)
 {
-  __shared__ double Rs[64 * 65];
+  __shared__ double Rs[64 * BS_RS];
   __shared__ __align__ (16) double vs[64];
+  __shared__ double rhs_s[64];
   __shared__ double accs[SWEEP_MAX_SLOTS][64];
   const int G = gridDim.x, me = blockIdx.x, T = sa.T, P = sa.nranks, q = sa.q;
   const bool sys = P > 1;
@@ -599,40 +653,47 @@ bsweep_kernel (const bsweep_args sa)
     return (I / P + (I % P > sa.rank ? 1 : 0)) * q;
   };
 
+  // inverse of the triangle of (owned) piece t -> Rs: 16 independent, fully coalesced loads per thread
   auto load_diag = [&] (int t) {
-    const int h = piece_h (t);
-    const size_t r0 = (size_t)t * 64, lr0 = (size_t)lidx_of (t) * 64;
+    const double *src = sa.V + (size_t)lidx_of (t) * 64 * 64;
     double r[16];
 #pragma unroll
     for (int u = 0; u < 16; u++)
-      {
-        const int e = threadIdx.x + 256 * u, i = e >> 6, j = e & 63;
-        r[u] = (i < h && j < h && j >= i) ? sa.A[(lr0 + i) * sa.ld + r0 + j] : 0.0;
-      }
+      r[u] = src[threadIdx.x + 256 * u];
 #pragma unroll
     for (int u = 0; u < 16; u++)
       {
-        const int e = threadIdx.x + 256 * u, i = e >> 6, j = e & 63;
-        Rs[i * 65 + j] = r[u];
+        const int e = threadIdx.x + 256 * u;
+        Rs[(e >> 6) * BS_RS + (e & 63)] = r[u];
       }
   };
 
   // this CTA owns piece t and its accumulator is complete: solve, store x_t everywhere, raise the flags
-  auto solve_and_publish = [&] (int t, bool diag_loaded) {
+  // dy: d_i y_i of the piece's rows (threads 0..63), fetched by the caller before it started to wait
+  auto solve_and_publish = [&] (int t, bool diag_loaded, double dy) {
     const int h = piece_h (t);
     const size_t r0 = (size_t)t * 64;
     if (!diag_loaded)
       load_diag (t);
     if (threadIdx.x < 64)
-      {
-        double rhs = 0.0;
-        if (threadIdx.x < h)
-          rhs = sa.d[r0 + threadIdx.x] * sa.y[r0 + threadIdx.x] - accs[lidx_of (t) / G][threadIdx.x];
-        vs[threadIdx.x] = rhs;
-      }
+      rhs_s[threadIdx.x] = threadIdx.x < h ? dy - accs[lidx_of (t) / G][threadIdx.x] : 0.0;
     __syncthreads ();
-    if (threadIdx.x < 32)
-      warp_tri_solve<false> (Rs, vs, h, sa.thresh, sa.flags);
+    {
+      // x_t = V_tt rhs: thread (row, g) takes columns 4 j + g; the zeros below the diagonal do no harm
+      const int row = threadIdx.x >> 2, g = threadIdx.x & 3;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 2)
+        {
+          s0 = fma (Rs[row * BS_RS + 4 * j + g], rhs_s[4 * j + g], s0);
+          s1 = fma (Rs[row * BS_RS + 4 * j + 4 + g], rhs_s[4 * j + 4 + g], s1);
+        }
+      double sx = s0 + s1;
+      sx += __shfl_xor_sync (0xffffffffu, sx, 1);
+      sx += __shfl_xor_sync (0xffffffffu, sx, 2);
+      if (g == 0)
+        vs[row] = row < h ? sx : 0.0;
+    }
     __syncthreads ();
     // x_t: own copy by threads 0..63, one peer per further group of 64 threads
     for (int e = threadIdx.x; e < 64 * P; e += 256)
@@ -680,8 +741,15 @@ bsweep_kernel (const bsweep_args sa)
       double buf0[16], buf1[16];
       // (the CTA on the critical path keeps only its critical block across the solve: registers)
       const int lc0 = lc, lc1 = (!ahead && lc >= G) ? lc - G : -1;
+      double dy = 0.0;  // d y of the piece this CTA solves in this iteration (threads 0..63)
       if (ahead)
-        load_diag (tn);
+        {
+          load_diag (tn);
+          if (threadIdx.x < 64 && (int)threadIdx.x < piece_h (tn))
+            dy = sa.d[(size_t)tn * 64 + threadIdx.x] * sa.y[(size_t)tn * 64 + threadIdx.x];
+        }
+      else if (mine && !solved_ahead && threadIdx.x < 64 && (int)threadIdx.x < h)
+        dy = sa.d[r0 + threadIdx.x] * sa.y[r0 + threadIdx.x];
       if (lc0 >= 0)
         bsweep_block_load (sa, (size_t)lc0 * 64, r0, h, buf0);
       if (lc1 >= 0)
@@ -689,7 +757,7 @@ bsweep_kernel (const bsweep_args sa)
       if (mine)
         {
           if (!solved_ahead)
-            solve_and_publish (t, false);  // vs = x_t afterwards
+            solve_and_publish (t, false, dy);  // vs = x_t afterwards
         }
       else
         {
@@ -708,7 +776,7 @@ bsweep_kernel (const bsweep_args sa)
           if (threadIdx.x < 64)
             vkeep = vs[threadIdx.x];
           __syncthreads ();  // accumulator of tn complete, vs saved
-          solve_and_publish (tn, true);
+          solve_and_publish (tn, true, dy);
           solved_ahead = true;
           if (threadIdx.x < 64)
             {
@@ -805,11 +873,14 @@ ms_k_sweep (ms_ctx *c, bool forward, double thresh, cudaStream_t s, int *done)
   int G = std::max (1, std::min (LT_all, max_bwd * c->sm_count));
   if ((LT_all + G - 1) / G > SWEEP_MAX_SLOTS)
     return MS_OK;  // rank-independent in practice (n / (64 P) chunks against 4 x 148 CTAs x 24 slots)
+  if (LT_all > 0 && !c->sweep_inv)
+    MS_CUDA (cudaMalloc (&c->sweep_inv, (size_t)LT_all * 64 * 64 * sizeof (double)));
   sa.A = c->A;
   sa.ld = c->ld;
   sa.n = c->n;
   sa.y = c->vec[MS_VEC_Y];
   sa.d = c->vec[MS_VEC_D];
+  sa.V = c->sweep_inv;
   sa.x = c->vec[MS_VEC_X];
   sa.ready = c->sweep_ready;
   sa.rank = c->rank;
@@ -824,6 +895,15 @@ ms_k_sweep (ms_ctx *c, bool forward, double thresh, cudaStream_t s, int *done)
   *done = 1;
   if (LT_all == 0)
     return MS_OK;  // more ranks than block rows: nothing to solve here, the peers still deliver x
+  const size_t inv_smem = 2 * 64 * 65 * sizeof (double);
+  static bool inv_configured[64] = {};
+  if (!inv_configured[c->device & 63])
+    {
+      MS_CUDA (cudaFuncSetAttribute (bsweep_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
+      inv_configured[c->device & 63] = true;
+    }
+  bsweep_invert_kernel<<<LT_all, 64, inv_smem, s>>> (c->A, c->ld, c->n, c->m, c->rank, c->nranks, c->sweep_inv, thresh, c->flags);
+  LAUNCH_COUNT (c);
   void *args[] = {(void *)&sa};
   MS_CUDA (cudaLaunchCooperativeKernel ((void *)bsweep_kernel, dim3 (G), dim3 (256), args, 0, s));
   LAUNCH_COUNT (c);

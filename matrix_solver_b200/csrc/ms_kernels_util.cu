@@ -97,7 +97,7 @@ constexpr int SYM_ROWS = 128;
 constexpr int SYM_COLS = 256;
 
 template <int MODE>
-__global__ void __launch_bounds__ (256)
+__global__ void __launch_bounds__ (256, 2)
 sym_onepass_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m, size_t rows_local, int rank,
                     int nranks, const double *__restrict__ x, double *__restrict__ rowS, double *__restrict__ rowA,
                     double *__restrict__ colS, double *__restrict__ colA)
@@ -105,8 +105,14 @@ sym_onepass_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m,
   constexpr bool NORM = MODE == MS_SYM_BNORM;
   __shared__ size_t grow[SYM_ROWS];
   __shared__ double wrow[SYM_ROWS];
-  __shared__ double cpart[8][SYM_COLS];
-  __shared__ double cpartA[NORM ? 8 : 1][SYM_COLS];
+  // dynamic shared memory: cpart[8][256] | rs[128][32] | (BNORM) cpartA[8][256] | rsA[128][32].
+  // The per-lane row accumulators rs live in shared memory (lane-private slots: bank = lane, no conflicts,
+  // no synchronisation): in registers they cost 64 of them and pushed the kernel to one CTA per SM.
+  extern __shared__ double sym_sm[];
+  double (*cpart)[SYM_COLS] = reinterpret_cast<double (*)[SYM_COLS]> (sym_sm);
+  double (*rs)[32] = reinterpret_cast<double (*)[32]> (sym_sm + 8 * SYM_COLS);
+  double (*cpartA)[SYM_COLS] = reinterpret_cast<double (*)[SYM_COLS]> (sym_sm + 8 * SYM_COLS + SYM_ROWS * 32);
+  double (*rsA)[32] = reinterpret_cast<double (*)[32]> (sym_sm + 16 * SYM_COLS + SYM_ROWS * 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t lr0 = (size_t)blockIdx.x * SYM_ROWS;
   if (tid < SYM_ROWS)
@@ -118,14 +124,13 @@ sym_onepass_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m,
     }
   __syncthreads ();
   const size_t c_first = (grow[0] / SYM_COLS) * SYM_COLS;  // global rows ascend inside a group
-  double racc[16], raccA[NORM ? 16 : 1];
 #pragma unroll
   for (int r = 0; r < 16; r++)
-    racc[r] = 0.0;
-  if (NORM)
-#pragma unroll
-    for (int r = 0; r < 16; r++)
-      raccA[r] = 0.0;
+    {
+      rs[warp * 16 + r][lane] = 0.0;
+      if (NORM)
+        rsA[warp * 16 + r][lane] = 0.0;
+    }
 
   for (size_t col0 = c_first; col0 < n; col0 += SYM_COLS)
     {
@@ -181,6 +186,7 @@ sym_onepass_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m,
               const int row = warp * 16 + r;
               const size_t gi = grow[row];
               const double wr = wrow[row];
+              double ra = 0.0, raA = 0.0;
 #pragma unroll
               for (int k = 0; k < 4; k++)
                 {
@@ -188,8 +194,8 @@ sym_onepass_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m,
                   // stored and counted: gi <= column < n  (gi == n for rows that do not exist)
                   const double a0 = (cj >= gi && cj < n) ? v[rr][k].x : 0.0;
                   const double a1 = (cj + 1 >= gi && cj + 1 < n) ? v[rr][k].y : 0.0;
-                  racc[r] = fma (a0, wc[k][0], racc[r]);
-                  racc[r] = fma (a1, wc[k][1], racc[r]);
+                  ra = fma (a0, wc[k][0], ra);
+                  ra = fma (a1, wc[k][1], ra);
                   // the mirrored element A(column, gi) exists only strictly above the diagonal
                   const double b0 = cj > gi ? a0 : 0.0;
                   const double b1 = cj + 1 > gi ? a1 : 0.0;
@@ -197,11 +203,15 @@ sym_onepass_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m,
                   cacc[k][1] = fma (b1, wr, cacc[k][1]);
                   if (NORM)
                     {
-                      raccA[r] += fabs (a0) + fabs (a1);
+                      raA += fabs (a0) + fabs (a1);
                       caccA[k][0] += fabs (b0);
                       caccA[k][1] += fabs (b1);
                     }
                 }
+              rs[row][lane] += ra;
+              if (NORM)
+                rsA[row][lane] += raA;
+              (void)r;
             }
         }
 #pragma unroll
@@ -235,7 +245,7 @@ sym_onepass_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m,
 #pragma unroll
   for (int r = 0; r < 16; r++)
     {
-      double s = racc[r], sa = NORM ? raccA[r] : 0.0;
+      double s = rs[warp * 16 + r][lane], sa = NORM ? rsA[warp * 16 + r][lane] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
         {
@@ -326,11 +336,19 @@ ms_k_sym_rows (ms_ctx *c, int mode, const double *xvec, double *out, double *nor
   unsigned gx = (unsigned)((n + 255) / 256);
   if (ngroups)
     {
+      const size_t sm1 = (8 * SYM_COLS + SYM_ROWS * 32) * sizeof (double);
+      static bool configured_dev[64] = {};
+      if (!configured_dev[c->device & 63])
+        {
+          MS_CUDA (cudaFuncSetAttribute (sym_onepass_kernel<MS_SYM_BNORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sm1)));
+          MS_CUDA (cudaFuncSetAttribute (sym_onepass_kernel<MS_SYM_SYMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+          configured_dev[c->device & 63] = true;
+        }
       if (mode == MS_SYM_BNORM)
-        sym_onepass_kernel<MS_SYM_BNORM><<<(unsigned)ngroups, 256, 0, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
+        sym_onepass_kernel<MS_SYM_BNORM><<<(unsigned)ngroups, 256, 2 * sm1, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
                                                                          c->nranks, xvec, rowS, rowA, colS, colA);
       else
-        sym_onepass_kernel<MS_SYM_SYMV><<<(unsigned)ngroups, 256, 0, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
+        sym_onepass_kernel<MS_SYM_SYMV><<<(unsigned)ngroups, 256, sm1, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
                                                                         c->nranks, xvec, rowS, rowA, colS, colA);
       LAUNCH_COUNT (c);
     }
