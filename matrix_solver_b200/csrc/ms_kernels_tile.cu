@@ -169,9 +169,8 @@ struct tile_pos
 // in the step-0 launch (profiles/r02_ncu_update_bsweep.txt, 2.09 x the algorithmic bytes).  Inside a band
 // the B slab is 64 column tiles (16 MB at K = 256) and stays in L2 while all row tiles pass over it; the
 // A slabs (128 KB per row tile) are re-read once per band.
-template <int MODE>
-__device__ __forceinline__ tile_pos
-tile_decode (const tile_args &ta, const int *prefF, int n_rt, int t)
+__device__ __forceinline__ int
+tile_band_of (const tile_args &ta, int t)
 {
   int b = 0, bh = ta.n_bands - 1;
   while (b < bh)
@@ -182,6 +181,17 @@ tile_decode (const tile_args &ta, const int *prefF, int n_rt, int t)
       else
         bh = mid - 1;
     }
+  return b;
+}
+
+// prefF[i] = sum of tile_first_in_row over row tiles [rbase, rbase + i): only the row tiles that START inside
+// the bands this CTA touches are ever looked up, so the prologue builds the prefix for those (<= 128 per band)
+// instead of for every row tile of the launch, and not at all for CTAs whose tiles lie in full-width rows.
+template <int MODE>
+__device__ __forceinline__ tile_pos
+tile_decode (const tile_args &ta, const int *prefF, int rbase, int t)
+{
+  const int b = tile_band_of (ta, t);
   const int lo_ct = b * ta.band_w;
   const int hi_ct = min (lo_ct + ta.band_w, tile_total_col_tiles (ta));
   const int wfull = hi_ct - lo_ct;
@@ -197,21 +207,21 @@ tile_decode (const tile_args &ta, const int *prefF, int n_rt, int t)
     {
       // row tiles [r1, r2) start inside the band: cum(rt) = tiles of [r1, rt) = (rt - r1) hi - (prefF[rt] - prefF[r1])
       o -= r1 * wfull;
+      const int *pf = prefF - rbase;
       int lo = r1, hi = r2 - 1;
       while (lo < hi)
         {
           const int mid = (lo + hi + 1) >> 1;
-          if ((mid - r1) * hi_ct - (prefF[mid] - prefF[r1]) <= o)
+          if ((mid - r1) * hi_ct - (pf[mid] - pf[r1]) <= o)
             lo = mid;
           else
             hi = mid - 1;
         }
       tp.rt = lo;
-      const int first = prefF[lo + 1] - prefF[lo];
-      tp.ct = (size_t)(first + (o - ((lo - r1) * hi_ct - (prefF[lo] - prefF[r1]))));
+      const int first = pf[lo + 1] - pf[lo];
+      tp.ct = (size_t)(first + (o - ((lo - r1) * hi_ct - (pf[lo] - pf[r1]))));
     }
   tp.g_row0 = tile_row_global (ta, MODE, tp.rt);
-  (void)n_rt;
   return tp;
 }
 
@@ -456,7 +466,6 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = ta.K / MS_KC;  // multiple of 4 (the host checks K % 64 == 0)
-  const int n_rt = ta.n_row_tiles;
 
   if (threadIdx.x == 0)
     {
@@ -474,14 +483,34 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
       sgn[k] = neg ? 0x80000000u : 0u;
       my_neg |= neg;
     }
-  for (int rt = threadIdx.x; rt < n_rt; rt += TILE_THREADS)
-    pref[rt + 1] = tile_first_in_row (ta, MODE, rt);
-  const bool any_neg = __syncthreads_or (my_neg) != 0;
-  if (warp == 0)
+  const int total_tiles = ta.band_start[ta.n_bands];
+  const int t_begin = blockIdx.x * ta.tiles_per_cta;
+  const int t_end = min (total_tiles, t_begin + ta.tiles_per_cta);
+  // which row tiles can the decode of THIS CTA's tiles look up?  Only those that start inside the band(s) of
+  // its first and last tile, and only if one of the tiles lies beyond the band's full-width rows.
+  int rbase = 0, rcnt = 0;
+  if (t_begin < t_end)
     {
-      // inclusive scan of pref[1..n_rt] by one warp: lane-contiguous segments
-      const int seg = (n_rt + 31) / 32;
-      const int b = lane * seg, e = min (b + seg, n_rt);
+      const int b0 = tile_band_of (ta, t_begin), b1 = tile_band_of (ta, t_end - 1);
+      const int total_ct = tile_total_col_tiles (ta);
+      const int w0 = min ((b0 + 1) * ta.band_w, total_ct) - b0 * ta.band_w;
+      const int w1 = min ((b1 + 1) * ta.band_w, total_ct) - b1 * ta.band_w;
+      const bool part = b0 != b1 || t_begin - ta.band_start[b0] >= ta.band_r1[b0] * w0
+                        || t_end - 1 - ta.band_start[b1] >= ta.band_r1[b1] * w1;
+      if (part)
+        {
+          rbase = ta.band_r1[b0];
+          rcnt = ta.band_r2[b1] - rbase;
+        }
+    }
+  for (int i = threadIdx.x; i < rcnt; i += TILE_THREADS)
+    pref[i + 1] = tile_first_in_row (ta, MODE, rbase + i);
+  const bool any_neg = __syncthreads_or (my_neg) != 0;
+  if (warp == 0 && rcnt > 0)
+    {
+      // inclusive scan of pref[1..rcnt] by one warp: lane-contiguous segments
+      const int seg = (rcnt + 31) / 32;
+      const int b = lane * seg, e = min (b + seg, rcnt);
       int sum = 0;
       for (int i = b; i < e; i++)
         sum += pref[i + 1];
@@ -504,7 +533,6 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
         pref[0] = 0;
     }
   __syncthreads ();
-  const int total_tiles = ta.band_start[ta.n_bands];
 
   const int p = lane >> 2, q = lane & 3;
   const int wm = warp >> 2;  // rows  wm*32
@@ -518,8 +546,6 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t a_e0 = a_base + off_e0, a_e1 = a_base + off_e1;
   const uint32_t b_e0 = b_base + off_e0, b_e1 = b_base + off_e1;
 
-  const int t_begin = blockIdx.x * ta.tiles_per_cta;
-  const int t_end = min (total_tiles, t_begin + ta.tiles_per_cta);
   const uint32_t n_chunks = t_end > t_begin ? (uint32_t)(t_end - t_begin) * (uint32_t)nkb : 0u;
 
   // producer state, advanced by thread 0 only: next chunk to request and where its operands are
@@ -527,7 +553,7 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
   int p_t = t_begin, p_kb = 0, p_ax = 0, p_ay = 0, p_bc = 0, p_ac = 0;
   if (threadIdx.x == 0 && n_chunks > 0)
     {
-      const tile_pos tp = tile_decode<MODE> (ta, pref, n_rt, p_t);
+      const tile_pos tp = tile_decode<MODE> (ta, pref, rbase, p_t);
       const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(tp.g_row0 / MS_CHUNK) : 0;
       p_ac = achunk0;
       p_ax = ta.ax0 + achunk0 * ta.axs;
@@ -538,7 +564,7 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t it = 0;  // chunks consumed so far by this CTA (all tiles)
   for (int t = t_begin; t < t_end; t++)
     {
-      const tile_pos tp = tile_decode<MODE> (ta, pref, n_rt, t);
+      const tile_pos tp = tile_decode<MODE> (ta, pref, rbase, t);
       const size_t g_row0 = tp.g_row0;
       const size_t col0 = tp.ct * MS_BN;
       const int rows_valid = g_row0 + MS_BM <= ta.n_rows ? MS_BM : (int)(ta.n_rows - g_row0);
@@ -608,7 +634,7 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
                           p_kb = 0;
                           if (++p_t < t_end)
                             {
-                              const tile_pos np = tile_decode<MODE> (ta, pref, n_rt, p_t);
+                              const tile_pos np = tile_decode<MODE> (ta, pref, rbase, p_t);
                               const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(np.g_row0 / MS_CHUNK) : 0;
                               p_ac = achunk0;
                               p_ax = ta.ax0 + achunk0 * ta.axs;
@@ -780,9 +806,10 @@ tile_build_bands (const ms_ctx *c, tile_args &ta, int mode)
 
 // Tiles per CTA.  Running CTAs are never preempted: the high-priority panel chain (diag, TRSM, the
 // next block row's update) only gets an SM slot when a low-priority tile CTA retires, so the CTA
-// lifetime is the chain's ramp-up latency.  With several GPUs the chain paces everybody
-// (profiles/README.md: 2 ms per chain with 4 tiles per CTA vs 0.3 ms on an idle GPU), so CTAs
-// walk a single tile there; on one GPU up to 4 tiles per CTA amortise the prologue (+1 %).
+// lifetime is the chain's ramp-up latency.  One tile per CTA everywhere since round 2: with the lean
+// prologue (band table in the kernel parameters, prefix built only for the rows a CTA can look up) walking
+// several tiles per CTA no longer pays — measured 2836 vs 2862 ms on one GPU and 1420 vs 1445 ms on two
+// (profiles/README.md); MS_TILES_PER_CTA overrides.
 static int g_tiles_per_cta_max = -1;
 static int
 tiles_per_cta_for (const ms_ctx *c, int total)
@@ -792,7 +819,7 @@ tiles_per_cta_for (const ms_ctx *c, int total)
       const char *e = getenv ("MS_TILES_PER_CTA");
       g_tiles_per_cta_max = e ? std::max (1, atoi (e)) : 0;
     }
-  int cap = g_tiles_per_cta_max > 0 ? g_tiles_per_cta_max : (c->nranks > 1 ? 1 : 4);
+  int cap = g_tiles_per_cta_max > 0 ? g_tiles_per_cta_max : 1;
   int t = total / (2 * c->sm_count * 8);
   return std::max (1, std::min (t, cap));
 }

@@ -1,15 +1,21 @@
 // ms_p2p.cu — see ms_p2p.h.
 #include <nccl.h>
 
+#include <algorithm>
+
 #include "ms_nccl.h"
 #include "ms_p2p.h"
 
 namespace
 {
-constexpr int SIG_INTS = 256;      // [I % 16] ready flag of panel I, [16 + r] credit from rank r
+constexpr int SIG_INTS = 256;      // [I % 16] ready flag of panel I, [16 + r] credit from rank r,
+                                   // [32 + (I % 4) * 16 + r] "rank r holds its slice of panel I"
 constexpr int SIG_READY = 0;
 constexpr int SIG_READY_SLOTS = 16;
 constexpr int SIG_CREDIT = 16;
+constexpr int SIG_SLICE = 32;
+constexpr int SIG_SLICE_SLOTS = 4;
+constexpr int SIG_MAX_RANKS = 16;
 constexpr int STAGE_SLOTS = 64;
 
 struct p2p_state
@@ -185,6 +191,8 @@ ms_p2p_init (ms_ctx *c)
   const size_t hb = sizeof (cudaIpcMemHandle_t);
   std::vector<char> mine (NH * hb, 0), all ((size_t)P * NH * hb);
   int bad = local_setup (c, p, mine) != MS_OK;
+  if (P > SIG_MAX_RANKS)
+    bad = 1;  // the flag page holds 16 ranks; larger jobs keep the NCCL transport
 
   // every rank walks the SAME collectives from here on, whatever failed locally: failures only set
   // `bad`, and the agreement below sends everybody to the NCCL transport together.  The exchange buffer
@@ -269,23 +277,58 @@ ms_p2p_begin_factor (ms_ctx *c)
     st (c)->epoch += (unsigned)c->nblocks + 8;
 }
 
-// PULL transport.  Pushing from the owner serialises on the owner's copy path (measured ~260 GB/s
-// aggregate for 7 peers, the last peer served 3.6 ms after the first at n = 65536); letting every
-// receiver pull with its own copy engine spreads the work over 7 engines and lets NVLink's egress
-// of the owner be the only shared resource.
-//   owner    : after the panel chain, raises ready[buffer] = epoch + I + 1 in every peer's memory
-//              (4-byte copies on per-peer streams; next owner first)
-//   receiver : panel stream waits for the flag, copies columns >= I*m of the owner's panel buffer and
-//              d_I into its own, then posts credit[rank] = epoch + I + 1 into the owner's memory
-//   owner    : before it writes the same buffer again (panel I+3, factored or pulled) it waits for all
-//              credits of panel I
-// The ready flag of panel I is word I % 16: with the rank counts of one box (2, 4, 8, 16 all divide 16)
-// every word has exactly one writer, the owner of block rows I, I+16, ..., whose posts are ordered on one
-// stream and only ever grow — a flag can never move backwards (round 1 shared one word per panel buffer
-// between different owners and relied on a timing margin).
+// PULL transport, scatter + all-gather.  Pushing from the owner serialises on the owner's copy path
+// (measured ~260 GB/s aggregate for 7 peers in round 1), so every receiver pulls with its own copy engine.
+// Round 2 measured what seven full-panel pulls out of ONE GPU cost: the owner's NVLink egress carries the
+// panel seven times (434 MB at r = 30k: ~0.56 ms of a 0.92 ms step cadence at 8 GPUs,
+// profiles/r02_trace_factor_8gpu_pull7.log).  Now the panel is cut into P-1 slices of 16-column chunks:
+//   owner      : after the panel chain, raises ready[I % 16] = epoch + I + 1 in every peer's memory
+//                (4-byte copies on per-peer streams; next owner first)
+//   receiver r : panel stream waits for the flag, pulls ITS slice (and d_I) out of the owner's buffer — the
+//                owner's egress carries the panel once —, credits the owner, tells every other receiver
+//                "slice r is here" (slice[I % 4][r] = epoch + I + 1), then pulls the other P-2 slices from
+//                the receivers that hold them (rotating start, so that every link is busy) and credits each
+//   any rank   : before it writes the same buffer again (panel I+3, factored or pulled) it waits for the
+//                credits of everybody who read panel I out of it: all peers if it owned panel I, the other
+//                receivers otherwise
+// Every flag word has exactly one writer whose posts are ordered on one stream and only ever grow (ready:
+// the owner of block rows I, I+16, ... for the rank counts of one box; slice and credit: rank r), so a
+// flag can never move backwards.
+namespace
+{
+struct span
+{
+  size_t off, cnt;  // doubles
+};
+
+// slice k (0 .. P-2) of the range of panel I that travels: 16-column chunks >= I*m / 16
+span
+panel_slice (const ms_ctx *c, size_t I, int k)
+{
+  const size_t chunk0 = (I * c->m) / MS_CHUNK, nch = c->ld / MS_CHUNK;
+  const size_t per = (nch - chunk0 + (size_t)(c->nranks - 2)) / (size_t)(c->nranks - 1);
+  const size_t a = std::min (nch, chunk0 + (size_t)k * per), b = std::min (nch, a + per);
+  return {a * c->hpb * MS_CHUNK, (b - a) * c->hpb * MS_CHUNK};
+}
+
+// receivers of panel I are numbered 0 .. P-2 starting with the next owner
+int
+receiver_index (const ms_ctx *c, int owner, int rank)
+{
+  return (rank - owner - 1 + c->nranks) % c->nranks;
+}
+
+int
+receiver_rank (const ms_ctx *c, int owner, int index)
+{
+  return (owner + 1 + index) % c->nranks;
+}
+}  // namespace
+
 int
 ms_p2p_send_panel (ms_ctx *c, size_t I, int pb, cudaEvent_t factored)
 {
+  (void)pb;
   p2p_state *p = st (c);
   const int P = c->nranks;
   for (int k = 1; k < P; k++)
@@ -304,31 +347,65 @@ int
 ms_p2p_wait_panel (ms_ctx *c, size_t I, int pb, int owner, cudaStream_t s)
 {
   p2p_state *p = st (c);
-  MS_TRY (wait_value (p, p->sig + SIG_READY + (int)(I % SIG_READY_SLOTS), p->epoch + (unsigned)I + 1, s));
+  const int P = c->nranks;
+  const unsigned stamp = p->epoch + (unsigned)I + 1;
+  MS_TRY (wait_value (p, p->sig + SIG_READY + (int)(I % SIG_READY_SLOTS), stamp, s));
   const bool has_trailing = (I + 1) * c->m < c->n;
-  const size_t chunk0 = (I * c->m) / MS_CHUNK;
-  const size_t off = chunk0 * c->hpb * MS_CHUNK;
-  const size_t cnt = (c->ld / MS_CHUNK - chunk0) * c->hpb * MS_CHUNK;
   const size_t rows = c->block_rows (I);
+  const int me = receiver_index (c, owner, c->rank);
   if (has_trailing)
-    MS_CUDA (cudaMemcpyAsync (c->PB[pb] + off, p->peer_pb[pb][owner] + off, cnt * sizeof (double), cudaMemcpyDefault, s));
+    {
+      const span sl = panel_slice (c, I, me);
+      if (sl.cnt)
+        MS_CUDA (cudaMemcpyAsync (c->PB[pb] + sl.off, p->peer_pb[pb][owner] + sl.off, sl.cnt * sizeof (double),
+                                  cudaMemcpyDefault, s));
+    }
   MS_CUDA (cudaMemcpyAsync (c->vec[MS_VEC_D] + I * c->m, p->peer_d[owner] + I * c->m, rows * sizeof (double),
                             cudaMemcpyDefault, s));
   // the owner may reuse its buffer once everybody has pulled
-  return post_value (p, c->nranks, p->peer_sig[owner] + SIG_CREDIT + c->rank, p->epoch + (unsigned)I + 1, s);
+  MS_TRY (post_value (p, P, p->peer_sig[owner] + SIG_CREDIT + c->rank, stamp, s));
+  if (!has_trailing || P <= 2)
+    return MS_OK;
+  // all-gather among the receivers: announce my slice first (nobody waits before everybody has posted)
+  int *slice_word = nullptr;
+  const int slot = SIG_SLICE + (int)(I % SIG_SLICE_SLOTS) * SIG_MAX_RANKS;
+  for (int j = 1; j < P - 1; j++)
+    {
+      const int r = receiver_rank (c, owner, (me + j) % (P - 1));
+      MS_TRY (post_value (p, P, p->peer_sig[r] + slot + c->rank, stamp, s));
+    }
+  for (int j = 1; j < P - 1; j++)
+    {
+      const int idx = (me + j) % (P - 1);
+      const int r = receiver_rank (c, owner, idx);
+      slice_word = p->sig + slot + r;
+      MS_TRY (wait_value (p, slice_word, stamp, s));
+      const span sl = panel_slice (c, I, idx);
+      if (sl.cnt)
+        MS_CUDA (cudaMemcpyAsync (c->PB[pb] + sl.off, p->peer_pb[pb][r] + sl.off, sl.cnt * sizeof (double),
+                                  cudaMemcpyDefault, s));
+      MS_TRY (post_value (p, P, p->peer_sig[r] + SIG_CREDIT + c->rank, stamp, s));
+    }
+  return MS_OK;
 }
 
-// before this rank writes PB[pb] at step I (factor or pull): if that buffer was the SOURCE of panel
-// I-3 (this rank owned it), every peer must have pulled it
+// before this rank writes PB[pb] at step I (factor or pull): everybody who read panel I-3 out of this
+// buffer must be done — all peers if this rank owned that panel, the other receivers (who fetched this
+// rank's slice here) otherwise
 int
 ms_p2p_before_overwrite (ms_ctx *c, size_t I, cudaStream_t s)
 {
   p2p_state *p = st (c);
-  if (I < MS_NPB || c->owner_of_block (I - MS_NPB) != c->rank)
+  if (I < MS_NPB)
+    return MS_OK;
+  const size_t J = I - MS_NPB;
+  const int owner = c->owner_of_block (J);
+  const bool sliced = (J + 1) * c->m < c->n && c->nranks > 2;
+  if (owner != c->rank && !sliced)
     return MS_OK;
   for (int r = 0; r < c->nranks; r++)
-    if (r != c->rank)
-      MS_TRY (wait_value (p, p->sig + SIG_CREDIT + r, p->epoch + (unsigned)(I - MS_NPB) + 1, s));
+    if (r != c->rank && (owner == c->rank || r != owner))
+      MS_TRY (wait_value (p, p->sig + SIG_CREDIT + r, p->epoch + (unsigned)J + 1, s));
   return MS_OK;
 }
 
@@ -338,7 +415,7 @@ ms_p2p_release_panel (ms_ctx *c, size_t I, cudaEvent_t freed)
   (void)c;
   (void)I;
   (void)freed;
-  return MS_OK;  // credits are posted by the pull itself
+  return MS_OK;  // credits are posted by the pulls themselves
 }
 
 // backward sweep over peer memory (ms_kernels_solve.cu): rank r's x vector and sweep flags as seen from here

@@ -90,17 +90,20 @@ class Graph:
 
 def build(nb, pieces, P, lookahead=True):
     """Replay of ms_factor (ms_api.cu) for all ranks.  Resources: ("row", J, p) = piece p of block row J,
-    ("pb", rank, b) = panel buffer b of a rank."""
+    ("pb", rank, b, k) = slice k of panel buffer b of a rank (the transport moves a panel as P-1 slices:
+    scatter from the owner, all-gather among the receivers — ms_p2p.cu)."""
     g = Graph()
     p2p = P > 1
-    info = {"diag": {}, "update": {}, "pull": {}, "panel_done": {}}
+    nsl = max(P - 1, 1)
+    info = {"diag": {}, "update": {}, "pull": {}, "pull2": {}, "panel_done": {}}
+    whole = lambda rank, pb: [("pb", rank, pb, k) for k in range(nsl)]
     for rank in range(P):
         sp, su, sm = ("sp", "su", "sm") if lookahead else ("sm", "sm", "sm")
         mine = lambda J: J < nb and J % P == rank
         ev_panel, ev_strip, ev_rest, ev_u2a, ev_free = {}, {}, {}, {}, {}
 
         def update(stream, I, pb, J, plist):
-            nid = g.node(rank, stream, f"upd p{I}->r{J}{plist}", reads=[("pb", rank, pb)],
+            nid = g.node(rank, stream, f"upd p{I}->r{J}{plist}", reads=whole(rank, pb),
                          writes=[("row", J, p) for p in plist])
             for p in plist:
                 info["update"].setdefault((J, p), []).append((I, nid))
@@ -114,10 +117,13 @@ def build(nb, pieces, P, lookahead=True):
             pb, owner = I % NPB, I % P
             if lookahead and I >= NPB:
                 g.wait(rank, sp, ev_free[I - NPB], f"wait free{I - NPB}")
-            if p2p and I >= NPB and (I - NPB) % P == rank:          # ms_p2p_before_overwrite
-                for r in range(P):
-                    if r != rank:
-                        g.wait_named(rank, sp, ("credit", I - NPB, r), f"wait credit p{I - NPB} from {r}")
+            if p2p and I >= NPB:                                     # ms_p2p_before_overwrite
+                J, jo = I - NPB, (I - NPB) % P
+                sliced = J < nb - 1 and P > 2
+                if jo == rank or sliced:
+                    for r in range(P):
+                        if r != rank and (jo == rank or r != jo):
+                            g.wait_named(rank, sp, ("credit", J, r, rank), f"wait credit p{J} from {r}")
             if owner == rank:
                 if lookahead and I > 0:
                     g.wait(rank, sp, ev_strip[I], f"wait strip{I}")
@@ -133,18 +139,32 @@ def build(nb, pieces, P, lookahead=True):
                     info["diag"][(I, t)] = d
                     if I == nb - 1 and t == pieces - 1:
                         continue                                     # nothing to the right of the last piece
-                    g.node(rank, sp, f"trsm r{I}.{t}", writes=[("row", I, t), ("pb", rank, pb)])
+                    g.node(rank, sp, f"trsm r{I}.{t}", writes=[("row", I, t)] + whole(rank, pb))
                     if lookahead and I > 0 and t == 0 and pieces > 1:
                         g.wait(rank, sp, ev_rest[I], f"wait rest{I}")
                         g.node(rank, sp, f"pretest r{I}.1..", reads=[("row", I, u) for u in range(1, pieces)])
                     if t + 1 < pieces:
-                        g.node(rank, sp, f"strip r{I}.{t}", reads=[("pb", rank, pb)],
+                        g.node(rank, sp, f"strip r{I}.{t}", reads=whole(rank, pb),
                                writes=[("row", I, u) for u in range(t + 1, pieces)])
             if p2p and owner != rank:                                # ms_p2p_wait_panel
                 g.wait_named(rank, sp, ("ready", I, rank), f"wait ready p{I}")
-                pull = g.node(rank, sp, f"pull p{I}", reads=[("pb", owner, pb)], writes=[("pb", rank, pb)])
+                me = (rank - owner - 1) % P                          # receiver index: my slice
+                trailing = I < nb - 1
+                pull = g.node(rank, sp, f"pull p{I} slice {me} from owner",
+                              reads=[("pb", owner, pb, me)] if trailing else [],
+                              writes=[("pb", rank, pb, me)] if trailing else [])
                 info["pull"][(I, rank)] = pull
-                g.named[("credit", I, rank)] = g.node(rank, sp, f"post credit p{I}")
+                g.named[("credit", I, rank, owner)] = g.node(rank, sp, f"post credit p{I} to owner")
+                if trailing and P > 2:
+                    g.named[("slice", I, rank)] = g.node(rank, sp, f"post slice p{I}.{me}")
+                    for j in range(1, P - 1):
+                        idx = (me + j) % (P - 1)
+                        r = (owner + 1 + idx) % P
+                        g.wait_named(rank, sp, ("slice", I, r), f"wait slice p{I}.{idx} at {r}")
+                        p2 = g.node(rank, sp, f"pull p{I} slice {idx} from {r}", reads=[("pb", r, pb, idx)],
+                                    writes=[("pb", rank, pb, idx)])
+                        info["pull2"][(I, rank, r)] = p2
+                        g.named[("credit", I, rank, r)] = g.node(rank, sp, f"post credit p{I} to {r}")
             ev_panel[I] = g.record(rank, sp)
             info["panel_done"][(I, rank)] = ev_panel[I]
             if lookahead:
@@ -174,7 +194,7 @@ def build(nb, pieces, P, lookahead=True):
                 first_rest = I + 3
             rest = [J for J in range(first_rest, nb) if mine(J)]     # U2b
             if rest:
-                nid = g.node(rank, sm, f"upd p{I}->rows{rest}", reads=[("pb", rank, pb)],
+                nid = g.node(rank, sm, f"upd p{I}->rows{rest}", reads=whole(rank, pb),
                              writes=[("row", J, p) for J in rest for p in range(pieces)])
                 for J in rest:
                     for p in range(pieces):
@@ -213,28 +233,37 @@ def test_factor_schedule_orders_every_conflict(nb, pieces, P):
                 assert a == b or hb(a, b), (J, p)
             if ups:
                 assert hb(ups[-1][1], d), (J, p)
-        # 3. a pull starts after the owner's whole panel chain of that block row
+        # 3. a pull starts after the owner's whole panel chain of that block row; a second-phase pull after the
+        #    serving receiver's own pull of that slice
         for (I, rank), pull in info["pull"].items():
             assert hb(info["panel_done"][(I, I % P)], pull), (I, rank)
+        for (I, rank, src), pull in info["pull2"].items():
+            assert hb(info["pull"][(I, src)], pull), (I, rank, src)
 
 
-def test_model_detects_a_missing_credit_wait():
-    """The checker is not vacuous: without the credit wait (ms_p2p_before_overwrite) the owner's
-    re-use of a panel buffer races with a peer's pull of the panel it held three steps earlier.  Five
-    ranks are needed to see it: with P <= 4 every peer owns one of the next three panels, and producing
-    that panel already implies that it pulled this one."""
+def test_model_detects_a_missing_slice_flag():
+    """The checker is not vacuous: without the "slice is here" flag a receiver's second-phase pull races with
+    the serving receiver's own pull of that slice out of the owner.  (The credits, by contrast, have become
+    redundant for P > 2: finishing panel I+1 anywhere needs every receiver's slice of it, hence every receiver's
+    completed step I — removing them leaves every conflict ordered, which the model confirms below.)"""
     P = 5
     g, info = build(11, 2, P)
-    # remove the edges credit -> owner's wait
+    for name, nid in g.deferred:
+        if name[0] == "slice":
+            g.succ[g.named[name]].discard(nid)
+    reach = g.reach()
+    hb = lambda a, b: bool(reach[a] >> b & 1) and a != b
+    races = sum(1 for (I, rank, src), p2 in info["pull2"].items()
+                if not hb(info["pull"][(I, src)], p2))
+    assert races > 0
+    g, info = build(11, 2, P)
     for name, nid in g.deferred:
         if name[0] == "credit":
             g.succ[g.named[name]].discard(nid)
     reach = g.reach()
     hb = lambda a, b: bool(reach[a] >> b & 1) and a != b
-    races = 0
-    for (I, rank), pull in info["pull"].items():
-        owner, pb = I % 2, I % NPB
+    for (I, rank, src), p2 in info["pull2"].items():
+        pb, idx = I % NPB, ((src - I % P - 1) % P)
         for nid, (r, _, label, _, writes) in enumerate(g.nodes):
-            if r == owner and ("pb", owner, pb) in writes and nid != pull and not (hb(nid, pull) or hb(pull, nid)):
-                races += 1
-    assert races > 0
+            if r == src and ("pb", src, pb, idx) in writes and nid != info["pull"][(I, src)]:
+                assert hb(nid, p2) or hb(p2, nid), (I, rank, src, label)
