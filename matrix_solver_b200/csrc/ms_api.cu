@@ -283,9 +283,6 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   e = getenv ("MS_PANEL_GEMM");
   if (e && atoi (e))
     c->panel_trsm = false;
-  e = getenv ("MS_TILE_RED");
-  if (e)
-    c->tile_red = atoi (e) != 0;
   e = getenv ("MS_NO_LOOKAHEAD");
   if (e && atoi (e))
     c->lookahead = false;
@@ -326,8 +323,6 @@ ms_set_option (ms_ctx *c, const char *key, long value)
     c->fuse_forward = value != 0 && c->aug_cols > 0;
   else if (!strcmp (key, "exact_pivots"))
     c->exact_pivots = value != 0;
-  else if (!strcmp (key, "tile_red"))
-    c->tile_red = value != 0;
   else if (!strcmp (key, "tile_band_w"))
     c->tile_band_w = (int)std::max (0l, value);
   else if (!strcmp (key, "tile_tma3"))

@@ -84,7 +84,6 @@ struct ms_ctx
                            // an augmented column (forward solve fused into the factorisation)
   bool fuse_forward = true;
   bool exact_pivots = false;  // diag kernel with the reference's sqrt / divide roundings ("exact_pivots" option)
-  bool tile_red = false;   // update epilogue through TMA bulk reductions ("tile_red" option / MS_TILE_RED)
   int tile_band_w = 0;     // column tiles per band of the tile walk (0 = default 64; "tile_band_w" option, tests)
   int aug_cols = 1;        // columns reserved right of column n-1 (0 only with MS_FUSE_FORWARD=0 at creation)
   unsigned long long b_version = 1;           // bumped whenever vec[B] is rewritten

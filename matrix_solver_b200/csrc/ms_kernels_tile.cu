@@ -60,7 +60,6 @@ struct tile_args
   size_t n;                 // columns >= n are never written
   size_t n_rows;            // rows >= n_rows do not exist (n < n_rows + 1 only without the augmented column)
   int tiles_per_cta;        // consecutive tiles one CTA walks before it retires
-  int red_epilogue;         // 1: interior tiles subtract through TMA bulk reductions (UPDATE mode, one tile per CTA)
   // L2-friendly rasterisation (host-built, tile_build_bands): the stored tiles are walked band by band
   // (band = band_w consecutive column tiles), row tile by row tile inside a band.  Band b starts at tile
   // band_start[b]; its first band_r1[b] row tiles own the whole band width, row tiles
@@ -668,43 +667,11 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
           it += MS_STAGES;
         }
 
-      // Interior tiles (all 64 x 128 entries stored) with one tile per CTA: C -= acc as C += (-acc) through TMA
-      // bulk reductions (cp.reduce.async.bulk ... add.f64, SASS UBLKRED.ADD.F64): the negated accumulators are
-      // staged in the now idle operand ring, every lane hands one 256-byte row of its warp's 32 x 32 patch to the
-      // copy unit, and the CTA retires as soon as the unit has READ the staging rows — the read-modify-write of C
-      // happens in L2, off the SM, instead of two dependent rounds of 16-byte loads, subtracts and stores per
-      // warp.  Same IEEE result (one rounded addition per entry; every entry belongs to exactly one tile).
-      if (MODE == MS_MODE_UPDATE && ta.red_epilogue && rows_valid == MS_BM && col0 >= col_lo && col0 + MS_BN <= ta.n)
-        {
-          constexpr int RS = 34;  // staging row stride in doubles: 272 bytes, 16-byte aligned
-          __syncthreads ();       // every warp has left the operand ring
-          double *stg = reinterpret_cast<double *> (smem) + warp * (32 * RS);
-#pragma unroll
-          for (int ib = 0; ib < 2; ib++)
-#pragma unroll
-            for (int a = 0; a < 2; a++)
-              {
-                double *row = stg + (16 * ib + 2 * p + a) * RS + 4 * q;
-#pragma unroll
-                for (int jb = 0; jb < 2; jb++)
-                  {
-                    *reinterpret_cast<double2 *> (row + 16 * jb) = make_double2 (-acc[ib][jb][a][0][0], -acc[ib][jb][a][1][0]);
-                    *reinterpret_cast<double2 *> (row + 16 * jb + 2) = make_double2 (-acc[ib][jb][a][0][1], -acc[ib][jb][a][1][1]);
-                  }
-              }
-          asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp ();
-          {
-            double *gdst = Ct + (size_t)(wm * 32 + lane) * ta.ldc + col0 + wn * 32;
-            const uint32_t ssrc = smem_u32 (stg + lane * RS);
-            asm volatile ("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 256;" ::"l"(gdst), "r"(ssrc)
-                          : "memory");
-            asm volatile ("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile ("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          }
-        }
-      else
-        tile_epilogue<MODE> (ta, acc, Ct, rows_valid, col0, col_lo, wm, wn, p, q);
+      // (An epilogue through TMA bulk reductions — C += (-acc) as cp.reduce.async.bulk add.f64 out of the idle
+      // operand ring, so that the read-modify-write happens in L2 — was built and measured in round 2: bit-identical,
+      // and no faster at K = 256, 128 or 64 (2833 vs 2824 ms, 55.98 vs 56.07 ms, 4.96 vs 4.98 ms).  The per-tile
+      // overhead at small K is the pipeline fill, not the epilogue; the variant was removed.)
+      tile_epilogue<MODE> (ta, acc, Ct, rows_valid, col0, col_lo, wm, wn, p, q);
     }
 }
 
@@ -894,7 +861,6 @@ ms_k_tile_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_en
       if (total == 0)
         continue;
       ta.tiles_per_cta = tiles_per_cta_for (c, total);
-      ta.red_epilogue = c->tile_red && ta.tiles_per_cta == 1;
       unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
       if (tile_tm3_ready (c))
         tile_dmma_kernel<MS_MODE_UPDATE, true><<<grid, TILE_THREADS, TILE_SMEM_BYTES, s>>> (

@@ -632,8 +632,11 @@ ms_probe_dmma_peak (int device, double *tflops)
   MS_CUDA (cudaGetDeviceProperties (&prop, device));
   double *d;
   MS_CUDA (cudaMalloc (&d, 64));
-  int iters = 4096;
-  int blocks = prop.multiProcessorCount * 4;
+  // Two CTAs of 8 warps per SM, all co-resident in one wave (74 registers): with four CTAs per SM only three fit
+  // at a time and the hardware's placement of the fourth made the result bimodal (37.1 or 29.7 TFLOP/s from
+  // process to process on the same box — round 2, profiles/README.md)
+  int iters = 8192;
+  int blocks = prop.multiProcessorCount * 2;
   cudaEvent_t e0, e1;
   MS_CUDA (cudaEventCreate (&e0));
   MS_CUDA (cudaEventCreate (&e1));

@@ -306,6 +306,88 @@ def test_tile_kernel_rank3_and_2d_tma_loads_agree(ms, n, m):
     for bw in (1, 3):
         alt = gpu_pipeline(ms, n, m, options=(("tile_band_w", bw),))
         assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 7, 1000, 4097):
+        v = rng.standard_normal(n)
+        assert ms.norm2(v) == pytest.approx(ora.norm2(v), rel=1e-14)
+        assert ms.error_vs_planted(v) == pytest.approx(ora.error(v), rel=1e-14)
+
+
+# --------------------------------------------------------------------------- whole pipeline, small
+@pytest.mark.parametrize("case", CASES)
+def test_pipeline_against_reference_golden(ms, case):
+    g = golden(case)
+    n, m = int(g["n"]), int(g["m"])
+    o = gpu_pipeline(ms, n, m, fixture_path(case))
+    assert np.array_equal(np.triu(o["A"]), g["A"])
+    assert o["norm"] == pytest.approx(float(g["norm"]), rel=4 * EPS)
+    assert np.allclose(o["b"], g["b"], rtol=n * EPS, atol=n * EPS * float(g["norm"]))
+    assert o["factor_fail"] == bool(g["factor_fail"])      # incl. b/c/d.txt: "Cant apply ..."
+    if o["factor_fail"]:
+        return
+    cond = cond_estimate(g["A"])
+    tol = C_TOL * n * EPS * cond
+    assert np.array_equal(o["d"], g["d"])                   # f.txt: d = (1, 1, -1, 1)
+    assert rel(np.triu(o["R"]), g["R"]) <= tol
+    assert not o["forward_fail"] and not o["backward_fail"]
+    assert rel(o["y"], g["y"]) <= tol
+    xstar = np.array([1.0 if i % 2 == 0 else 0.0 for i in range(n)])
+    assert o["error"] <= max(2 * float(g["error"]), tol * np.linalg.norm(xstar))
+    bn = np.linalg.norm(g["b"])
+    assert o["residual"] / bn <= max(2 * float(g["residual"]) / bn, 8 * n * EPS)
+
+
+@pytest.mark.parametrize("n,m", [(3, 3), (5, 1), (9, 2), (17, 5), (30, 30), (33, 64), (65, 64), (127, 64),
+                                 (129, 64), (192, 64), (200, 64), (257, 128), (300, 100), (511, 192)])
+def test_pipeline_against_oracle_formula_sweep(ms, ora, n, m):
+    """The reference's own sweep idea (test_data/test13_mpi.sh): many (n, m), incl. n % m != 0,
+    m > n, m == n — both kernel families (m % 64 == 0 -> DMMA tiles, otherwise generic)."""
+    o = gpu_pipeline(ms, n, m)
+    w = ora.solve_pipeline(n, m)
+    assert np.array_equal(np.triu(o["A"]), np.triu(w["A"]))
+    assert o["norm"] == w["norm"] and np.array_equal(o["b"], w["b"])   # integer data: exact
+    assert not o["factor_fail"] and np.array_equal(o["d"], w["d"])
+    tol = C_TOL * n * EPS * 1.62 * n * n
+    assert rel(np.triu(o["R"]), np.triu(w["R"])) <= tol
+    assert rel(o["y"], w["y"]) <= tol and rel(o["x"], w["x"]) <= tol
+    assert o["error"] <= max(2 * w["error"], tol * np.sqrt(n))
+    assert o["residual"] <= max(2 * w["residual"], 8 * n * EPS * np.linalg.norm(w["b"]))
+    assert o["stats"]["used_dmma"] == (1 if (m % 64 == 0 and n > 64) else 0)
+    # the r vector itself (find_disrep_vec, src/init.cpp:533-563): its 2-norm is the reported residual and
+    # every entry is rounding noise of the size the reference's own r has
+    assert np.isclose(np.linalg.norm(o["r"]), o["residual"], rtol=1e-12, atol=0)
+    assert np.max(np.abs(o["r"])) <= max(4 * np.max(np.abs(w["r"])), 8 * n * EPS * np.max(np.abs(w["b"])))
+
+
+@pytest.mark.parametrize("opts", [(("force_generic", 1),), (("lookahead", 0),), (("force_generic", 1), ("lookahead", 0)),
+                                  (("panel_trsm", 0),), (("panel_trsm", 0), ("force_generic", 1)),
+                                  (("single_launch_sweeps", 0),)])
+def test_kernel_families_and_schedules_agree(ms, opts):
+    """DMMA tiles vs generic DFMA kernel, look-ahead vs in-order: same factor within rounding."""
+    n, m = 640, 128
+    base = gpu_pipeline(ms, n, m)
+    alt = gpu_pipeline(ms, n, m, options=opts)
+    tol = C_TOL * n * EPS * 1.62 * n * n
+    assert rel(np.triu(alt["R"]), np.triu(base["R"])) <= tol
+    assert rel(alt["x"], base["x"]) <= tol
+    if ("lookahead", 0) in opts and ("force_generic", 1) not in opts:
+        assert np.array_equal(alt["R"], base["R"])           # scheduling must not change arithmetic
+
+
+@pytest.mark.parametrize("n,m", [(640, 128), (1024, 256), (2048, 64), (1000, 192)])
+def test_tile_kernel_rank3_and_2d_tma_loads_agree(ms, n, m):
+    """The update launches feed the tile kernel through a rank-3 tensor map over the chunk-major panel
+    buffer (three TMA instructions per stage); "tile_tma3" = 0 selects the twelve 2-D loads that land
+    the same shared-memory image.  Same DMMA sequence per accumulator, so factor and solution must be
+    bit-identical — also with negative d (sign flips) through the dense upload path."""
+    base = gpu_pipeline(ms, n, m)
+    alt = gpu_pipeline(ms, n, m, options=(("tile_tma3", 0),))
+    assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
+    # the order in which the stored tiles are walked (bands of "tile_band_w" column tiles; 64 by default,
+    # i.e. a single band at these n) must not change a bit either: 1 and 3 give many bands here
+    for bw in (1, 3):
+        alt = gpu_pipeline(ms, n, m, options=(("tile_band_w", bw),))
+        assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
     # the two epilogues — read-modify-write in registers, or C += (-acc) through TMA bulk reductions
     # (UBLKRED.ADD.F64 in L2) for interior tiles — round once per entry and must agree bit for bit
     for red in (0, 1):
