@@ -60,6 +60,7 @@ struct tile_args
   size_t n;                 // columns >= n are never written
   size_t n_rows;            // rows >= n_rows do not exist (n < n_rows + 1 only without the augmented column)
   int tiles_per_cta;        // consecutive tiles one CTA walks before it retires
+  int early_issue;          // 1: thread 0 requests the first operand chunks before the rest of the prologue (MS_TILE_EARLY=0: A/B)
   // L2-friendly rasterisation (host-built, tile_build_bands): the stored tiles are walked band by band
   // (band = band_w consecutive column tiles), row tile by row tile inside a band.  Band b starts at tile
   // band_start[b]; its first band_r1[b] row tiles own the whole band width, row tiles
@@ -467,22 +468,6 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = ta.K / MS_KC;  // multiple of 4 (the host checks K % 64 == 0)
 
-  if (threadIdx.x == 0)
-    {
-      for (int s = 0; s < MS_STAGES; s++)
-        {
-          mbar_init (&full_bar[s], 1);
-          mbar_init (&empty_bar[s], MS_TILE_CONSUMER_WARPS);
-        }
-      mbar_fence_init ();
-    }
-  int my_neg = 0;
-  for (int k = threadIdx.x; k < ta.K; k += TILE_THREADS)
-    {
-      const bool neg = ta.dsign != nullptr && ta.dsign[k] < 0.0;
-      sgn[k] = neg ? 0x80000000u : 0u;
-      my_neg |= neg;
-    }
   const int total_tiles = ta.band_start[ta.n_bands];
   const int t_begin = blockIdx.x * ta.tiles_per_cta;
   const int t_end = min (total_tiles, t_begin + ta.tiles_per_cta);
@@ -502,6 +487,80 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
           rbase = ta.band_r1[b0];
           rcnt = ta.band_r2[b1] - rbase;
         }
+    }
+  const uint32_t n_chunks = t_end > t_begin ? (uint32_t)(t_end - t_begin) * (uint32_t)nkb : 0u;
+
+  // producer state, advanced by thread 0 only: next chunk to request and where its operands are
+  uint32_t pj = 0;
+  int p_t = t_begin, p_kb = 0, p_ax = 0, p_ay = 0, p_bc = 0, p_ac = 0;
+  auto producer_seek = [&] () {
+    const tile_pos tp = tile_decode<MODE> (ta, pref, rbase, p_t);
+    const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(tp.g_row0 / MS_CHUNK) : 0;
+    p_ac = achunk0;
+    p_ax = ta.ax0 + achunk0 * ta.axs;
+    p_ay = ta.ay0 + achunk0 * ta.ays;
+    p_bc = (int)(tp.ct * (MS_BN / MS_CHUNK));
+  };
+  // request every chunk up to number `upto` (thread 0): wait until its stage is free, arm the barrier, issue the loads
+  auto request = [&] (uint32_t upto) {
+    while (pj < n_chunks && pj <= upto)
+      {
+        const uint32_t ps = pj & (MS_STAGES - 1);
+        mbar_wait (&empty_bar[ps], ((pj >> 2) & 1u) ^ 1u);
+        mbar_arrive_expect_tx (&full_bar[ps], TILE_STAGE_BYTES);
+        uint8_t *sa = smem + ps * TILE_STAGE_BYTES;
+        uint8_t *sb = sa + TILE_A_BYTES;
+        const int kk = p_kb * MS_KC;
+        if (MODE == MS_MODE_UPDATE && TM3)
+          {
+            // rank-3 view of the chunk-major panel buffer: coordinates (column in chunk, k row,
+            // chunk); a box holds four chunks, so a stage is three instructions, not twelve
+            tma_load_3d (sa, &tm3, 0, ta.ay0 + kk, p_ac, &full_bar[ps]);
+            tma_load_3d (sb, &tm3, 0, ta.by0 + kk, p_bc, &full_bar[ps]);
+            tma_load_3d (sb + 4 * TILE_CHUNK_BYTES, &tm3, 0, ta.by0 + kk, p_bc + 4, &full_bar[ps]);
+          }
+        else
+          {
+#pragma unroll
+            for (int ci = 0; ci < MS_BM / MS_CHUNK; ci++)
+              tma_load_2d (sa + ci * TILE_CHUNK_BYTES, &tmA, p_ax + ci * ta.axs, p_ay + ci * ta.ays + kk, &full_bar[ps]);
+#pragma unroll
+            for (int cj = 0; cj < MS_BN / MS_CHUNK; cj++)
+              tma_load_2d (sb + cj * TILE_CHUNK_BYTES, &tmB, ta.bx0 + (p_bc + cj) * ta.bxs,
+                           ta.by0 + (p_bc + cj) * ta.bys + kk, &full_bar[ps]);
+          }
+        pj++;
+        if (++p_kb == nkb)
+          {
+            p_kb = 0;
+            if (++p_t < t_end)
+              producer_seek ();
+          }
+      }
+  };
+  if (threadIdx.x == 0)
+    {
+      for (int s = 0; s < MS_STAGES; s++)
+        {
+          mbar_init (&full_bar[s], 1);
+          mbar_init (&empty_bar[s], MS_TILE_CONSUMER_WARPS);
+        }
+      mbar_fence_init ();
+      // The first three chunks are requested NOW, before the rest of the prologue (sign words from global memory,
+      // two CTA barriers): the ~1 us until the first stage lands is the longest item of a tile's fixed cost and
+      // hides behind the prologue this way.  Only CTAs whose tiles need the prefix array have to wait for it.
+      if (n_chunks > 0 && rcnt == 0 && ta.early_issue)
+        {
+          producer_seek ();
+          request (TILE_AHEAD);
+        }
+    }
+  int my_neg = 0;
+  for (int k = threadIdx.x; k < ta.K; k += TILE_THREADS)
+    {
+      const bool neg = ta.dsign != nullptr && ta.dsign[k] < 0.0;
+      sgn[k] = neg ? 0x80000000u : 0u;
+      my_neg |= neg;
     }
   for (int i = threadIdx.x; i < rcnt; i += TILE_THREADS)
     pref[i + 1] = tile_first_in_row (ta, MODE, rbase + i);
@@ -546,20 +605,8 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t a_e0 = a_base + off_e0, a_e1 = a_base + off_e1;
   const uint32_t b_e0 = b_base + off_e0, b_e1 = b_base + off_e1;
 
-  const uint32_t n_chunks = t_end > t_begin ? (uint32_t)(t_end - t_begin) * (uint32_t)nkb : 0u;
-
-  // producer state, advanced by thread 0 only: next chunk to request and where its operands are
-  uint32_t pj = 0;
-  int p_t = t_begin, p_kb = 0, p_ax = 0, p_ay = 0, p_bc = 0, p_ac = 0;
-  if (threadIdx.x == 0 && n_chunks > 0)
-    {
-      const tile_pos tp = tile_decode<MODE> (ta, pref, rbase, p_t);
-      const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(tp.g_row0 / MS_CHUNK) : 0;
-      p_ac = achunk0;
-      p_ax = ta.ax0 + achunk0 * ta.axs;
-      p_ay = ta.ay0 + achunk0 * ta.ays;
-      p_bc = (int)(tp.ct * (MS_BN / MS_CHUNK));
-    }
+  if (threadIdx.x == 0 && n_chunks > 0 && (rcnt > 0 || !ta.early_issue))
+    producer_seek ();  // (the other CTAs did this, and requested their first chunks, at the top of the kernel)
 
   uint32_t it = 0;  // chunks consumed so far by this CTA (all tiles)
   for (int t = t_begin; t < t_end; t++)
@@ -599,51 +646,7 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int s = 0; s < MS_STAGES; s++)
             {
               if (threadIdx.x == 0)
-                {
-                  // request chunks up to it + s + TILE_AHEAD (three at the very start, then one per chunk)
-                  while (pj < n_chunks && pj <= it + (uint32_t)s + TILE_AHEAD)
-                    {
-                      const uint32_t ps = pj & (MS_STAGES - 1);
-                      mbar_wait (&empty_bar[ps], ((pj >> 2) & 1u) ^ 1u);
-                      mbar_arrive_expect_tx (&full_bar[ps], TILE_STAGE_BYTES);
-                      uint8_t *sa = smem + ps * TILE_STAGE_BYTES;
-                      uint8_t *sb = sa + TILE_A_BYTES;
-                      const int kk = p_kb * MS_KC;
-                      if (MODE == MS_MODE_UPDATE && TM3)
-                        {
-                          // rank-3 view of the chunk-major panel buffer: coordinates (column in chunk, k row,
-                          // chunk); a box holds four chunks, so a stage is three instructions, not twelve
-                          tma_load_3d (sa, &tm3, 0, ta.ay0 + kk, p_ac, &full_bar[ps]);
-                          tma_load_3d (sb, &tm3, 0, ta.by0 + kk, p_bc, &full_bar[ps]);
-                          tma_load_3d (sb + 4 * TILE_CHUNK_BYTES, &tm3, 0, ta.by0 + kk, p_bc + 4, &full_bar[ps]);
-                        }
-                      else
-                        {
-#pragma unroll
-                          for (int ci = 0; ci < MS_BM / MS_CHUNK; ci++)
-                            tma_load_2d (sa + ci * TILE_CHUNK_BYTES, &tmA, p_ax + ci * ta.axs,
-                                         p_ay + ci * ta.ays + kk, &full_bar[ps]);
-#pragma unroll
-                          for (int cj = 0; cj < MS_BN / MS_CHUNK; cj++)
-                            tma_load_2d (sb + cj * TILE_CHUNK_BYTES, &tmB, ta.bx0 + (p_bc + cj) * ta.bxs,
-                                         ta.by0 + (p_bc + cj) * ta.bys + kk, &full_bar[ps]);
-                        }
-                      pj++;
-                      if (++p_kb == nkb)
-                        {
-                          p_kb = 0;
-                          if (++p_t < t_end)
-                            {
-                              const tile_pos np = tile_decode<MODE> (ta, pref, rbase, p_t);
-                              const int achunk0 = MODE == MS_MODE_UPDATE ? (int)(np.g_row0 / MS_CHUNK) : 0;
-                              p_ac = achunk0;
-                              p_ax = ta.ax0 + achunk0 * ta.axs;
-                              p_ay = ta.ay0 + achunk0 * ta.ays;
-                              p_bc = (int)(np.ct * (MS_BN / MS_CHUNK));
-                            }
-                        }
-                    }
-                }
+                request (it + (uint32_t)s + TILE_AHEAD);  // three chunks at the very start, then one per chunk
               mbar_wait (&full_bar[s], ph);
               const uint32_t *sgn_chunk = sgn + (kb4 + s) * MS_KC + 2 * q;
               if (njb < 2)
@@ -814,6 +817,18 @@ tile_build_bands (const ms_ctx *c, tile_args &ta, int mode)
 // prologue (band table in the kernel parameters, prefix built only for the rows a CTA can look up) walking
 // several tiles per CTA no longer pays — measured 2836 vs 2862 ms on one GPU and 1420 vs 1445 ms on two
 // (profiles/README.md); MS_TILES_PER_CTA overrides.
+static int
+tile_early_issue ()
+{
+  static int v = -1;
+  if (v < 0)
+    {
+      const char *e = getenv ("MS_TILE_EARLY");
+      v = e ? atoi (e) != 0 : 1;
+    }
+  return v;
+}
+
 static int g_tiles_per_cta_max = -1;
 static int
 tiles_per_cta_for (const ms_ctx *c, int total)
@@ -861,6 +876,7 @@ ms_k_tile_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_en
       if (total == 0)
         continue;
       ta.tiles_per_cta = tiles_per_cta_for (c, total);
+      ta.early_issue = tile_early_issue ();
       unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
       if (tile_tm3_ready (c))
         tile_dmma_kernel<MS_MODE_UPDATE, true><<<grid, TILE_THREADS, TILE_SMEM_BYTES, s>>> (
@@ -908,6 +924,7 @@ ms_k_tile_panel (ms_ctx *c, int pb, const ms_piece &pc, size_t I, cudaStream_t s
   if (total == 0)
     return MS_OK;
   ta.tiles_per_cta = tiles_per_cta_for (c, total);
+  ta.early_issue = tile_early_issue ();
   unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
   tile_dmma_kernel<MS_MODE_PANEL, false><<<grid, TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, c->tm_A, ta);
   LAUNCH_COUNT (c);
