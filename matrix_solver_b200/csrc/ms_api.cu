@@ -544,7 +544,9 @@ packed_transfer (ms_ctx *c, double *body, int to_packed)
       while (i0 < rows_total)
         {
           size_t i1 = i0;
-          while (i1 < rows_total && row_off (i1 + 1) - row_off (i0) <= c->stage_doubles)
+          // (one grid row per matrix row in the scatter/gather kernel: at most 65535 of them per segment — narrow
+          // block columns of a large matrix would otherwise fit more rows into the staging buffer than a grid has)
+          while (i1 < rows_total && i1 - i0 < 65535 && row_off (i1 + 1) - row_off (i0) <= c->stage_doubles)
             i1++;
           MS_CHECK_ARG (i1 > i0, "one row of a block column exceeds the staging buffer");
           size_t seg_base = row_off (i0);

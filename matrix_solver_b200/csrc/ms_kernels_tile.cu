@@ -60,7 +60,6 @@ struct tile_args
   size_t n;                 // columns >= n are never written
   size_t n_rows;            // rows >= n_rows do not exist (n < n_rows + 1 only without the augmented column)
   int tiles_per_cta;        // consecutive tiles one CTA walks before it retires
-  int early_issue;          // 1: thread 0 requests the first operand chunks before the rest of the prologue (MS_TILE_EARLY=0: A/B)
   // L2-friendly rasterisation (host-built, tile_build_bands): the stored tiles are walked band by band
   // (band = band_w consecutive column tiles), row tile by row tile inside a band.  Band b starts at tile
   // band_start[b]; its first band_r1[b] row tiles own the whole band width, row tiles
@@ -547,9 +546,10 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       mbar_fence_init ();
       // The first three chunks are requested NOW, before the rest of the prologue (sign words from global memory,
-      // two CTA barriers): the ~1 us until the first stage lands is the longest item of a tile's fixed cost and
-      // hides behind the prologue this way.  Only CTAs whose tiles need the prefix array have to wait for it.
-      if (n_chunks > 0 && rcnt == 0 && ta.early_issue)
+      // two CTA barriers), so that the ~1 us until the first stage lands overlaps it.  Only CTAs whose tiles need the
+      // prefix array have to wait for it.  (Measured neutral with two CTAs per SM — 2819.8 vs 2820.1 ms at n = 65536,
+      // 56.5 vs 56.3 ms at n = 16384, m = 128: the other CTA's DMMA loop already covers the fill.)
+      if (n_chunks > 0 && rcnt == 0)
         {
           producer_seek ();
           request (TILE_AHEAD);
@@ -605,7 +605,7 @@ tile_dmma_kernel (const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t a_e0 = a_base + off_e0, a_e1 = a_base + off_e1;
   const uint32_t b_e0 = b_base + off_e0, b_e1 = b_base + off_e1;
 
-  if (threadIdx.x == 0 && n_chunks > 0 && (rcnt > 0 || !ta.early_issue))
+  if (threadIdx.x == 0 && n_chunks > 0 && rcnt > 0)
     producer_seek ();  // (the other CTAs did this, and requested their first chunks, at the top of the kernel)
 
   uint32_t it = 0;  // chunks consumed so far by this CTA (all tiles)
@@ -817,18 +817,6 @@ tile_build_bands (const ms_ctx *c, tile_args &ta, int mode)
 // prologue (band table in the kernel parameters, prefix built only for the rows a CTA can look up) walking
 // several tiles per CTA no longer pays — measured 2836 vs 2862 ms on one GPU and 1420 vs 1445 ms on two
 // (profiles/README.md); MS_TILES_PER_CTA overrides.
-static int
-tile_early_issue ()
-{
-  static int v = -1;
-  if (v < 0)
-    {
-      const char *e = getenv ("MS_TILE_EARLY");
-      v = e ? atoi (e) != 0 : 1;
-    }
-  return v;
-}
-
 static int g_tiles_per_cta_max = -1;
 static int
 tiles_per_cta_for (const ms_ctx *c, int total)
@@ -876,7 +864,6 @@ ms_k_tile_update (ms_ctx *c, int pb, size_t I, size_t lrow_begin, size_t lrow_en
       if (total == 0)
         continue;
       ta.tiles_per_cta = tiles_per_cta_for (c, total);
-      ta.early_issue = tile_early_issue ();
       unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
       if (tile_tm3_ready (c))
         tile_dmma_kernel<MS_MODE_UPDATE, true><<<grid, TILE_THREADS, TILE_SMEM_BYTES, s>>> (
@@ -924,7 +911,6 @@ ms_k_tile_panel (ms_ctx *c, int pb, const ms_piece &pc, size_t I, cudaStream_t s
   if (total == 0)
     return MS_OK;
   ta.tiles_per_cta = tiles_per_cta_for (c, total);
-  ta.early_issue = tile_early_issue ();
   unsigned grid = (unsigned)((total + ta.tiles_per_cta - 1) / ta.tiles_per_cta);
   tile_dmma_kernel<MS_MODE_PANEL, false><<<grid, TILE_THREADS, TILE_SMEM_BYTES, s>>> (c->tm_Wt, c->tm_A, c->tm_A, ta);
   LAUNCH_COUNT (c);
