@@ -96,7 +96,7 @@ ms_k_fill_formula (ms_ctx *c, int kind, cudaStream_t s)
 constexpr int SYM_ROWS = 128;
 constexpr int SYM_COLS = 256;
 
-template <int MODE>
+template <int MODE, int RB>
 __global__ void __launch_bounds__ (256, 2)
 sym_onepass_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m, size_t rows_local, int rank,
                     int nranks, const double *__restrict__ x, double *__restrict__ rowS, double *__restrict__ rowA,
@@ -161,7 +161,6 @@ sym_onepass_kernel (const double *__restrict__ A, size_t ld, size_t n, size_t m,
         }
       // rows go in batches of RB: all loads of a batch are issued before its arithmetic (RB x 4 16-byte
       // loads in flight per lane; a warp-uniform `continue` per row would serialise the rows' latencies)
-      constexpr int RB = NORM ? 2 : 4;
 #pragma unroll
       for (int rb = 0; rb < 16; rb += RB)
         {
@@ -340,15 +339,25 @@ ms_k_sym_rows (ms_ctx *c, int mode, const double *xvec, double *out, double *nor
       static bool configured_dev[64] = {};
       if (!configured_dev[c->device & 63])
         {
-          MS_CUDA (cudaFuncSetAttribute (sym_onepass_kernel<MS_SYM_BNORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sm1)));
-          MS_CUDA (cudaFuncSetAttribute (sym_onepass_kernel<MS_SYM_SYMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+          MS_CUDA (cudaFuncSetAttribute (sym_onepass_kernel<MS_SYM_BNORM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sm1)));
+          MS_CUDA (cudaFuncSetAttribute (sym_onepass_kernel<MS_SYM_BNORM, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sm1)));
+          MS_CUDA (cudaFuncSetAttribute (sym_onepass_kernel<MS_SYM_SYMV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
           configured_dev[c->device & 63] = true;
         }
-      if (mode == MS_SYM_BNORM)
-        sym_onepass_kernel<MS_SYM_BNORM><<<(unsigned)ngroups, 256, 2 * sm1, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
-                                                                         c->nranks, xvec, rowS, rowA, colS, colA);
+      static int rb_norm = -1;  // rows per load batch in BNORM mode (2: 48 bytes of spills; 4: 156, twice the loads in flight)
+      if (rb_norm < 0)
+        {
+          const char *e = getenv ("MS_SYM_RB");
+          rb_norm = e && atoi (e) == 2 ? 2 : 4;
+        }
+      if (mode == MS_SYM_BNORM && rb_norm == 2)
+        sym_onepass_kernel<MS_SYM_BNORM, 2><<<(unsigned)ngroups, 256, 2 * sm1, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
+                                                                            c->nranks, xvec, rowS, rowA, colS, colA);
+      else if (mode == MS_SYM_BNORM)
+        sym_onepass_kernel<MS_SYM_BNORM, 4><<<(unsigned)ngroups, 256, 2 * sm1, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
+                                                                            c->nranks, xvec, rowS, rowA, colS, colA);
       else
-        sym_onepass_kernel<MS_SYM_SYMV><<<(unsigned)ngroups, 256, sm1, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
+        sym_onepass_kernel<MS_SYM_SYMV, 4><<<(unsigned)ngroups, 256, sm1, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
                                                                         c->nranks, xvec, rowS, rowA, colS, colA);
       LAUNCH_COUNT (c);
     }
