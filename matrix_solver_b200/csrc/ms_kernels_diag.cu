@@ -644,28 +644,32 @@ ms_k_pretest (ms_ctx *c, const double *diag0, size_t ld, int first, int count, d
 // into the panel buffer.  This is what DRtA / DRtA_l (src/matrix_op.cpp:287-368) compute with the
 // explicit inverse; here it is a true triangular solve, one thread per column:
 //     x_i = (a_i - sum_{k<i} R_ki x_k) / R_ii,   row i then scaled by d_i.
-// R (64 x 64, upper) is staged in shared memory (transposed: RT[i][k] = R(k, i)) and read with 16-byte
-// broadcast loads; the CTA's 64 x 128 slab of the block row sits in shared memory too, one column per thread
-// (column tid of every row: conflict-free, and private to its thread).  The solve is blocked by 8 rows and
-// right-looking: the 8 x 8 triangle of a block is solved out of registers (28 FMAs), then the rows below lose
-// R(block, k)^T x_block — 8 FMAs per row in two independent chains.  Both loops are ROLLED: the round-1 kernel
-// was one straight line of ~5000 instructions per thread (2016 FMAs fully unrolled so that x[64] could live in
-// registers) and ncu showed `no_instruction` — instruction-cache misses — among its top stalls at one warp per
-// scheduler; this one is ~150 instructions of code.  Loads/stores are coalesced across the warp (adjacent
+// R (64 x 64, upper) is staged in shared memory and read with 16-byte broadcast loads; each thread
+// keeps its column in registers (right-looking: after x_i, rows k > i lose R_ik x_i — 63 independent
+// FMAs, so the kernel runs at DFMA issue rate).  Loads/stores are coalesced across the warp (adjacent
 // threads = adjacent columns): 16 B of HBM traffic per element + 8 B for the panel-buffer copy.
+// (Round 2 tried a version blocked by 8 rows with rolled loops and the slab's partial sums in shared memory —
+// 700 instead of 5000 instructions, 60 instead of 200 registers: 26.6 us against this kernel's 22 us at 16k
+// columns.  With one warp per scheduler the kernel is bound by dependent-operation latency, and keeping the
+// whole column in registers with four independent FMA chains beats the shared-memory round trips.)
 __global__ void __launch_bounds__ (128, 2)
 trsm_panel_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restrict__ rows, size_t ld, int h, size_t col_lo,
                    size_t n, const double *__restrict__ dpiece, double *__restrict__ PB, size_t pb_H, size_t pb_k0)
 {
+  // RT[i][k] = R(k, i) for k < i (the column of R that row i of the solve needs), 0 elsewhere
   constexpr int RS = MS_SUB + 2;  // row stride: even (16-byte loads) and not a multiple of 32 banks
   __shared__ __align__ (16) double RT[MS_SUB * RS];
   __shared__ double rinv[MS_SUB], ds[MS_SUB];
   extern __shared__ double As[];  // [MS_SUB][128]: the CTA's slab of the block row
-  const size_t j = col_lo + (size_t)blockIdx.x * 128 + threadIdx.x;
-  // stage the slab first: every thread has its 64 loads in flight at once
+  const size_t j0 = col_lo + (size_t)blockIdx.x * 128;
+  // stage the slab first: every thread has its 64 loads in flight at once (the serial solve below
+  // would otherwise wait one HBM round trip per row)
 #pragma unroll 16
   for (int k = 0; k < MS_SUB; k++)
-    As[k * 128 + threadIdx.x] = (k < h && j < n) ? rows[(size_t)k * ld + j] : 0.0;
+    {
+      const size_t j = j0 + threadIdx.x;
+      As[k * 128 + threadIdx.x] = (k < h && j < n) ? rows[(size_t)k * ld + j] : 0.0;
+    }
   for (int e = threadIdx.x; e < MS_SUB * MS_SUB; e += 128)
     {
       const int k = e >> 6, i = e & 63;  // coalesced read of row k of R
@@ -678,64 +682,37 @@ trsm_panel_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restri
       ds[i] = i < h ? dpiece[i] : 1.0;
     }
   __syncthreads ();
+  const size_t j = j0 + threadIdx.x;
   if (j >= n)
     return;
-  double *mine = As + threadIdx.x;  // my column: mine[k * 128]
+  double x[MS_SUB];
   double *pcol = rows + j;
   double *ppb = PB + chunk_major_index (pb_k0, j, pb_H);
-#pragma unroll 1
-  for (int i0 = 0; i0 < MS_SUB; i0 += 8)
+#pragma unroll
+  for (int i = 0; i < MS_SUB; i++)
     {
-      if (i0 >= h)
-        break;
-      double x[8];
+      // four interleaved partial sums keep four independent FMA chains in flight
+      double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
-      for (int r = 0; r < 8; r++)
-        x[r] = mine[(i0 + r) * 128];
-      // 8 x 8 triangle: x_r = (rhs_r - sum_{q<r} R(i0+q, i0+r) x_q) / R(i0+r, i0+r)
-#pragma unroll
-      for (int r = 0; r < 8; r++)
+      for (int k = 0; k < (i & ~3); k += 4)
         {
-          const double *rt = &RT[(i0 + r) * RS + i0];
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int q = 0; q + 1 < r; q += 2)
-            {
-              const double2 rv = *reinterpret_cast<const double2 *> (rt + q);
-              s0 = fma (rv.x, x[q], s0);
-              s1 = fma (rv.y, x[q + 1], s1);
-            }
-          if (r & 1)
-            s0 = fma (rt[r - 1], x[r - 1], s0);
-          x[r] = (x[r] - (s0 + s1)) * rinv[i0 + r];
+          const double2 ra = *reinterpret_cast<const double2 *> (&RT[i * RS + k]);
+          const double2 rb = *reinterpret_cast<const double2 *> (&RT[i * RS + k + 2]);
+          p0 = fma (ra.x, x[k], p0);
+          p1 = fma (ra.y, x[k + 1], p1);
+          p2 = fma (rb.x, x[k + 2], p2);
+          p3 = fma (rb.y, x[k + 3], p3);
         }
 #pragma unroll
-      for (int r = 0; r < 8; r++)
-        if (i0 + r < h)
-          {
-            const double val = x[r] * ds[i0 + r];
-            pcol[(size_t)(i0 + r) * ld] = val;
-            ppb[(size_t)(i0 + r) * MS_CHUNK] = val;  // next k row of the same 16-column chunk
-          }
-      // rows below the block: rhs_k -= sum_q R(i0+q, k) x_q
-#pragma unroll 2
-      for (int k = i0 + 8; k < h; k++)
+      for (int k = (i & ~3); k < i; k++)
+        p0 = fma (RT[i * RS + k], x[k], p0);
+      const double xi = (As[i * 128 + threadIdx.x] - ((p0 + p1) + (p2 + p3))) * rinv[i];
+      x[i] = xi;
+      if (i < h)
         {
-          const double *rt = &RT[k * RS + i0];
-          const double2 r01 = *reinterpret_cast<const double2 *> (rt);
-          const double2 r23 = *reinterpret_cast<const double2 *> (rt + 2);
-          const double2 r45 = *reinterpret_cast<const double2 *> (rt + 4);
-          const double2 r67 = *reinterpret_cast<const double2 *> (rt + 6);
-          double t0 = mine[k * 128], t1 = 0.0;
-          t0 = fma (-r01.x, x[0], t0);
-          t1 = fma (-r01.y, x[1], t1);
-          t0 = fma (-r23.x, x[2], t0);
-          t1 = fma (-r23.y, x[3], t1);
-          t0 = fma (-r45.x, x[4], t0);
-          t1 = fma (-r45.y, x[5], t1);
-          t0 = fma (-r67.x, x[6], t0);
-          t1 = fma (-r67.y, x[7], t1);
-          mine[k * 128] = t0 + t1;
+          const double val = xi * ds[i];
+          pcol[(size_t)i * ld] = val;
+          ppb[(size_t)i * MS_CHUNK] = val;   // next k row of the same 16-column chunk
         }
     }
 }

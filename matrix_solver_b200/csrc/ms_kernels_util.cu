@@ -339,21 +339,12 @@ ms_k_sym_rows (ms_ctx *c, int mode, const double *xvec, double *out, double *nor
       static bool configured_dev[64] = {};
       if (!configured_dev[c->device & 63])
         {
-          MS_CUDA (cudaFuncSetAttribute (sym_onepass_kernel<MS_SYM_BNORM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sm1)));
           MS_CUDA (cudaFuncSetAttribute (sym_onepass_kernel<MS_SYM_BNORM, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sm1)));
           MS_CUDA (cudaFuncSetAttribute (sym_onepass_kernel<MS_SYM_SYMV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
           configured_dev[c->device & 63] = true;
         }
-      static int rb_norm = -1;  // rows per load batch in BNORM mode (2: 48 bytes of spills; 4: 156, twice the loads in flight)
-      if (rb_norm < 0)
-        {
-          const char *e = getenv ("MS_SYM_RB");
-          rb_norm = e && atoi (e) == 2 ? 2 : 4;
-        }
-      if (mode == MS_SYM_BNORM && rb_norm == 2)
-        sym_onepass_kernel<MS_SYM_BNORM, 2><<<(unsigned)ngroups, 256, 2 * sm1, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
-                                                                            c->nranks, xvec, rowS, rowA, colS, colA);
-      else if (mode == MS_SYM_BNORM)
+      // four rows per load batch in both modes (BNORM: 5.7 vs 6.1 ms with two, measured at n = 65536)
+      if (mode == MS_SYM_BNORM)
         sym_onepass_kernel<MS_SYM_BNORM, 4><<<(unsigned)ngroups, 256, 2 * sm1, s>>> (c->A, c->ld, n, c->m, c->rows_local, c->rank,
                                                                             c->nranks, xvec, rowS, rowA, colS, colA);
       else
