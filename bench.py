@@ -455,6 +455,9 @@ def our_arm(args):
         "config": {"workload": f"formula-generated SPD A_ij=n-max(i,j), n={n}, block m={m}, factor+solve "
                                f"(BASELINE configs[{CONFIG_INDEX.get((n, m), '-')}]); block-row cyclic over {world} GPU(s)",
                    "n": n, "m": m,
+                   # rows per block row the kernels walked: m, or the internal 256 a single GPU uses for m = 64 / 128
+                   # (same R and d)
+                   "block_internal": int(st1["block_internal"]),
                    "parallelism": f"block-row-cyclic x{world}, look-ahead 2, panel over NVLink peer memory "
                                   f"(copy engines; ncclBroadcast when MS_P2P=0)" if world > 1 else "single GPU, look-ahead 2",
                    "forward_solve": "fused into the factorisation (b as augmented column)" if forward_fused

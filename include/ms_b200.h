@@ -62,6 +62,9 @@ typedef struct ms_stats
   int forward_fused;      /* 1 if the last ms_solve_forward only read back the y that ms_factor carried
                              along as an augmented column (no sweep over R) */
   double update_sum_ms;   /* plain sum of the same intervals (look-ahead lets two of them overlap) */
+  int block_internal;     /* rows per block row the last ms_factor walked: m, or the internal blocking (256) a
+                             single-GPU context uses for m = 64 / 128 on the tensor-core path (same R and d, the
+                             reference's pivot pre-tests still per m rows; MS_SUPER_BLOCK=0 switches it off) */
 } ms_stats;
 
 /* ---- library / error state -------------------------------------------------- */

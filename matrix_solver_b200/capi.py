@@ -28,6 +28,7 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("used_dmma", C.c_int),
         ("forward_fused", C.c_int),
         ("update_sum_ms", C.c_double),
+        ("block_internal", C.c_int),
     ]
 
     def as_dict(self):

@@ -106,6 +106,25 @@ build_pieces (ms_ctx *c)
   c->block_first_piece[c->nblocks] = c->pieces.size ();
 }
 
+// Switch the blocking the kernels walk (m_api <-> m_super, one GPU only: local row == global row under either).
+// The matrix storage does not depend on it — rows x ld with everything right of the diagonal meaningful — and
+// the panel buffers were sized for the taller panel at creation, so only the block / piece tables change.
+static void
+set_blocking (ms_ctx *c, size_t m_new)
+{
+  if (m_new == c->m)
+    return;
+  c->m = m_new;
+  c->nblocks = c->n / m_new + (c->n % m_new > 0);
+  build_pieces (c);
+}
+
+static size_t
+wanted_blocking (const ms_ctx *c)
+{
+  return (c->m_super && c->fast && !c->force_generic && !c->exact_pivots) ? c->m_super : c->m_api;
+}
+
 static int
 ctx_free (ms_ctx *c)
 {
@@ -173,6 +192,7 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   ms_ctx *c = new ms_ctx ();
   c->n = n;
   c->m = m;
+  c->m_api = m;
   c->device = device;
   c->rank = rank;
   c->nranks = nranks;
@@ -186,6 +206,25 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   c->ncols = n + (size_t)c->aug_cols;
   c->hpb = round_up (m, MS_SUB);
   c->fast = (m % MS_SUB == 0 && m <= 1024);  // the tile kernel keeps K = m sign words in shared memory
+  // Internal blocking (one GPU, tensor-core path): the K = 64 / 128 trailing update runs at 19 % / 74 % of the
+  // DMMA peak against 89 % at K = 256 (profiles/README.md), and which rows form a block row is invisible in R
+  // and d.  A caller's m = 64 or 128 is therefore factored in block rows of 256: the same chain of 64-row pieces,
+  // the reference's per-block-row pivot pre-test still taken per m rows (factor_block_row), one update of depth
+  // 256 instead of four of depth 64.  Ownership would change with several ranks, so P = 1 only; the
+  // exact-arithmetic modes ("force_generic", "exact_pivots", the block API) keep the caller's blocking.
+  // MS_SUPER_BLOCK=0 switches it off, another multiple of m (<= 1024) selects that.
+  if (nranks == 1 && c->fast)
+    {
+      size_t want = 256;
+      const char *sb = getenv ("MS_SUPER_BLOCK");
+      if (sb)
+        want = (size_t)atol (sb);
+      if (want > m && want % m == 0 && want <= 1024)
+        {
+          c->m_super = want;
+          c->hpb = round_up (want, MS_SUB);  // the panel buffers are laid out for the taller panel from the start
+        }
+    }
   c->rows_local = 0;
   for (size_t I = rank; I < c->nblocks; I += (size_t)nranks)
     c->rows_local += c->block_rows (I);
@@ -283,6 +322,9 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   e = getenv ("MS_PANEL_GEMM");
   if (e && atoi (e))
     c->panel_trsm = false;
+  e = getenv ("MS_LEFT_LOOKING");
+  if (e && !atoi (e))
+    c->left_looking = false;
   e = getenv ("MS_NO_LOOKAHEAD");
   if (e && atoi (e))
     c->lookahead = false;
@@ -310,19 +352,30 @@ ms_set_option (ms_ctx *c, const char *key, long value)
       MS_CUDA (cudaSetDevice (c->device));
       if (c->profile_update && c->prof_pool.empty ())
         {
-          c->prof_pool.resize (2 * (4 * c->nblocks + 8));
+          c->prof_pool.resize (2 * (4 * (c->n / c->m_api + 1) + 8));
           for (auto &e : c->prof_pool)
             MS_CUDA (cudaEventCreate (&e));
         }
     }
   else if (!strcmp (key, "panel_trsm"))
     c->panel_trsm = value != 0;
+  else if (!strcmp (key, "left_looking"))
+    c->left_looking = value != 0;
   else if (!strcmp (key, "single_launch_sweeps"))
     c->no_sweep = value == 0;
   else if (!strcmp (key, "fuse_forward"))
     c->fuse_forward = value != 0 && c->aug_cols > 0;
   else if (!strcmp (key, "exact_pivots"))
     c->exact_pivots = value != 0;
+  else if (!strcmp (key, "super_block"))
+    {
+      // 0 = factor in block rows of the caller's m; otherwise a multiple of m the panel buffers were sized for
+      MS_CHECK_ARG (value == 0
+                      || (c->nranks == 1 && c->fast && value > 0 && (size_t)value % c->m_api == 0
+                          && round_up ((size_t)value, MS_SUB) <= c->hpb),
+                    "super_block: 0, or a multiple of m within the panel buffers of this context (one GPU)");
+      c->m_super = (size_t)value > c->m_api ? (size_t)value : 0;
+    }
   else if (!strcmp (key, "tile_band_w"))
     c->tile_band_w = (int)std::max (0l, value);
   else if (!strcmp (key, "tile_tma3"))
@@ -418,13 +471,16 @@ stage_h2d (ms_ctx *c, int half, const double *src, size_t cnt)
 static int
 rows_dma (ms_ctx *c, double *rows, size_t row0, size_t nrows, size_t ld_host, bool to_device, bool wait = true)
 {
-  for (size_t I = row0 / c->m; I < c->nblocks && I * c->m < row0 + nrows; I++)
+  // block rows of the CALLER's m (with an internal blocking the rows lie where they always do — one GPU —, and
+  // "from the start of each row's diagonal block" keeps the meaning the header gives it)
+  const size_t ma = c->m_api, nba = c->n / ma + (c->n % ma > 0);
+  for (size_t I = row0 / ma; I < nba && I * ma < row0 + nrows; I++)
     {
       if (c->owner_of_block (I) != c->rank)
         continue;
-      size_t g0 = std::max (I * c->m, row0);
-      size_t g1 = std::min (I * c->m + c->block_rows (I), row0 + nrows);
-      size_t col0 = I * c->m;
+      size_t g0 = std::max (I * ma, row0);
+      size_t g1 = std::min (std::min ((I + 1) * ma, c->n), row0 + nrows);
+      size_t col0 = I * ma;
       double *dev = c->row_ptr (g0) + col0;
       double *host = rows + (g0 - row0) * ld_host + col0;
       size_t width = (c->n - col0) * sizeof (double);
@@ -526,13 +582,14 @@ static int
 packed_transfer (ms_ctx *c, double *body, int to_packed)
 {
   MS_CUDA (cudaSetDevice (c->device));
-  const size_t n = c->n, m = c->m;
+  const size_t n = c->n, m = c->m_api;  // the reference's layout: block columns of the caller's m
+  const size_t nb_api = n / m + (n % m > 0);
   size_t base = 0;
   bool pinned = is_pinned_host (body);
   int half = 0;
-  for (size_t J = 0; J < c->nblocks; J++)
+  for (size_t J = 0; J < nb_api; J++)
     {
-      size_t w = c->block_rows (J);  // column width == height of block row J
+      size_t w = std::min (m, n - J * m);  // column width == height of block row J
       size_t rows_total = J * m + w;
       auto row_off = [&] (size_t i) -> size_t {
         if (i <= J * m)
@@ -793,16 +850,37 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s, cu
       const ms_piece &pc = c->pieces[pi];
       // the block row's pre-update pivot test (src/solver.cpp:117) rides along with its first piece's
       // diag kernel — except that with look-ahead the later pieces receive their last update (panel
-      // I-1) only at `rest_ready`: their share of the test runs right after that wait, below
+      // I-1) only at `rest_ready`: their share of the test runs right after that wait, below.
+      // "Block row" here is the CALLER's: with an internal blocking (c->m a multiple of m_api) the test
+      // of rows [k0, k0 + m_api) is taken when the piece that opens them comes up, i.e. after the pieces
+      // above it have been applied to them — the state the reference tests them in.
+      const size_t k0 = pc.row0 - I * c->m;
       const bool first = pi == c->block_first_piece[I];
+      const bool sub_first = k0 % c->m_api == 0;
+      const size_t sub_rows = std::min (c->m_api, rowsI - k0);
       const bool split_pre = first && rest_ready != nullptr && (size_t)pc.h < rowsI;
-      const double *pre = first ? diag0 : nullptr;
-      const int pre_count = first ? (split_pre ? pc.h : (int)rowsI) : 0;
+      const double *pre = sub_first ? diag0 + k0 * (c->ld + 1) : nullptr;
+      const int pre_count = sub_first ? (split_pre ? pc.h : (int)sub_rows) : 0;
       double *blk = c->A + pc.lrow0 * c->ld + pc.row0;
       double *rows = c->A + pc.lrow0 * c->ld;
       size_t col_lo = pc.row0 + (size_t)pc.h;
-      size_t k0 = pc.row0 - I * c->m;
       const bool tiles = c->fast && !c->force_generic;
+      // Inside the block row the tensor-core path works left-looking: a piece receives the pieces above it in ONE
+      // update of depth K = 64, 128, 192 right before its diag kernel, instead of every factored piece being pushed
+      // into all rows below it with K = 64 (where the tile kernel runs at a fifth of its K = 256 rate) — the same
+      // flops in deeper, smaller launches, and a shorter dependent chain.  The piece that opens one of the CALLER's
+      // block rows brings all of that block row's rows up to date (they are pre-tested with it, see above); the
+      // pieces after it then only lack the pieces of their own caller block row.  The exact-arithmetic kernels keep
+      // the right-looking order.
+      const bool left = tiles && c->left_looking;
+      if (left && k0 > 0)
+        {
+          const size_t ksub = k0 / c->m_api * c->m_api;
+          if (sub_first)
+            MS_TRY (do_update (c, pb, I, pc.lrow0, pc.lrow0 + sub_rows, (int)k0, 0, s, false));
+          else if (k0 > ksub)
+            MS_TRY (do_update (c, pb, I, pc.lrow0, pc.lrow0 + (size_t)pc.h, (int)(k0 - ksub), ksub, s, false));
+        }
       if (c->panel_trsm)
         {
           // K1 then K3 as a triangular solve: no explicit inverse on the critical path
@@ -839,9 +917,10 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s, cu
       if (rest_ready && first && lr_next < lr_end)
         {
           MS_CUDA (cudaStreamWaitEvent (s, rest_ready, 0));
-          MS_TRY (ms_k_pretest (c, diag0, c->ld, pc.h, (int)rowsI, thresh, s));
+          MS_TRY (ms_k_pretest (c, diag0, c->ld, pc.h, (int)std::min (c->m_api, rowsI), thresh, s));
         }
-      MS_TRY (do_update (c, pb, I, lr_next, lr_end, pc.h, k0, s, false));
+      if (!left)
+        MS_TRY (do_update (c, pb, I, lr_next, lr_end, pc.h, k0, s, false));
     }
   return MS_OK;
 }
@@ -860,6 +939,8 @@ ms_factor (ms_ctx *c, double norma, double *elapsed_s)
   MS_CHECK_ARG (c, "null ctx");
   MS_CUDA (cudaSetDevice (c->device));
   const double thresh = 1.e-14 * norma;  // EPS * norma, src/defines.h:9
+  set_blocking (c, wanted_blocking (c));
+  c->stats.block_internal = (int)c->m;
   const size_t nb = c->nblocks;
   const int P = c->nranks;
   const bool la = c->lookahead;

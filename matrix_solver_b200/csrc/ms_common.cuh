@@ -76,7 +76,12 @@ struct ms_piece
 
 struct ms_ctx
 {
-  size_t n = 0, m = 0;
+  size_t n = 0, m = 0;     // m = the blocking the kernels currently walk (see m_api / m_super)
+  size_t m_api = 0;        // the caller's block size: the reference's semantics (packed layout, which rows a
+                           // block row's pre-update pivot test covers, row transfers) follow this one
+  size_t m_super = 0;      // 0, or the internal blocking of the tensor-core path when the caller's m is a
+                           // small multiple of 64 on one GPU: block rows of m_super rows are factored in 64-row
+                           // pieces exactly as before, but the trailing update then runs with K = m_super
   int device = 0, rank = 0, nranks = 1;
   size_t nblocks = 0;      // block rows: n/m + (n%m > 0)
   size_t ld = 0;           // leading dimension (doubles), multiple of 16, >= n + 1
@@ -97,6 +102,9 @@ struct ms_ctx
   bool profile_update = false;
   bool trace = false;       // MS_TRACE=1: timing-enabled step events, read back by ms_debug_trace
   std::vector<float> trace_panel, trace_free, trace_strip;
+  bool left_looking = true; // inside a block row the tensor-core path updates each 64-row piece just before it is
+                            // factored, with all pieces above it at once (K = 64, 128, 192) — instead of pushing every
+                            // factored piece into all rows below it (K = 64 each time); "left_looking" option
   bool panel_trsm = true;   // K3 as a triangular solve (default) or as a DMMA product with the inverse
 
   double *A = nullptr;       // rows_alloc x ld, row-major; only j >= i meaningful

@@ -516,7 +516,7 @@ ms_k_packed_rows (ms_ctx *c, double *d_seg, size_t J, size_t w, size_t i0, size_
   if (i1 <= i0)
     return MS_OK;
   dim3 grid ((unsigned)((w + 255) / 256), (unsigned)(i1 - i0));
-  packed_copy_kernel<<<grid, 256, 0, s>>> (c->A, c->ld, c->m, c->rank, c->nranks, d_seg, J, w, i0, i1,
+  packed_copy_kernel<<<grid, 256, 0, s>>> (c->A, c->ld, c->m_api, c->rank, c->nranks, d_seg, J, w, i0, i1,
                                           seg_base, to_packed);
   LAUNCH_COUNT (c);
   MS_CUDA (cudaGetLastError ());

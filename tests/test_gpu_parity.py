@@ -307,88 +307,6 @@ def test_tile_kernel_rank3_and_2d_tma_loads_agree(ms, n, m):
         alt = gpu_pipeline(ms, n, m, options=(("tile_band_w", bw),))
         assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
     rng = np.random.default_rng(5)
-    for n in (1, 2, 7, 1000, 4097):
-        v = rng.standard_normal(n)
-        assert ms.norm2(v) == pytest.approx(ora.norm2(v), rel=1e-14)
-        assert ms.error_vs_planted(v) == pytest.approx(ora.error(v), rel=1e-14)
-
-
-# --------------------------------------------------------------------------- whole pipeline, small
-@pytest.mark.parametrize("case", CASES)
-def test_pipeline_against_reference_golden(ms, case):
-    g = golden(case)
-    n, m = int(g["n"]), int(g["m"])
-    o = gpu_pipeline(ms, n, m, fixture_path(case))
-    assert np.array_equal(np.triu(o["A"]), g["A"])
-    assert o["norm"] == pytest.approx(float(g["norm"]), rel=4 * EPS)
-    assert np.allclose(o["b"], g["b"], rtol=n * EPS, atol=n * EPS * float(g["norm"]))
-    assert o["factor_fail"] == bool(g["factor_fail"])      # incl. b/c/d.txt: "Cant apply ..."
-    if o["factor_fail"]:
-        return
-    cond = cond_estimate(g["A"])
-    tol = C_TOL * n * EPS * cond
-    assert np.array_equal(o["d"], g["d"])                   # f.txt: d = (1, 1, -1, 1)
-    assert rel(np.triu(o["R"]), g["R"]) <= tol
-    assert not o["forward_fail"] and not o["backward_fail"]
-    assert rel(o["y"], g["y"]) <= tol
-    xstar = np.array([1.0 if i % 2 == 0 else 0.0 for i in range(n)])
-    assert o["error"] <= max(2 * float(g["error"]), tol * np.linalg.norm(xstar))
-    bn = np.linalg.norm(g["b"])
-    assert o["residual"] / bn <= max(2 * float(g["residual"]) / bn, 8 * n * EPS)
-
-
-@pytest.mark.parametrize("n,m", [(3, 3), (5, 1), (9, 2), (17, 5), (30, 30), (33, 64), (65, 64), (127, 64),
-                                 (129, 64), (192, 64), (200, 64), (257, 128), (300, 100), (511, 192)])
-def test_pipeline_against_oracle_formula_sweep(ms, ora, n, m):
-    """The reference's own sweep idea (test_data/test13_mpi.sh): many (n, m), incl. n % m != 0,
-    m > n, m == n — both kernel families (m % 64 == 0 -> DMMA tiles, otherwise generic)."""
-    o = gpu_pipeline(ms, n, m)
-    w = ora.solve_pipeline(n, m)
-    assert np.array_equal(np.triu(o["A"]), np.triu(w["A"]))
-    assert o["norm"] == w["norm"] and np.array_equal(o["b"], w["b"])   # integer data: exact
-    assert not o["factor_fail"] and np.array_equal(o["d"], w["d"])
-    tol = C_TOL * n * EPS * 1.62 * n * n
-    assert rel(np.triu(o["R"]), np.triu(w["R"])) <= tol
-    assert rel(o["y"], w["y"]) <= tol and rel(o["x"], w["x"]) <= tol
-    assert o["error"] <= max(2 * w["error"], tol * np.sqrt(n))
-    assert o["residual"] <= max(2 * w["residual"], 8 * n * EPS * np.linalg.norm(w["b"]))
-    assert o["stats"]["used_dmma"] == (1 if (m % 64 == 0 and n > 64) else 0)
-    # the r vector itself (find_disrep_vec, src/init.cpp:533-563): its 2-norm is the reported residual and
-    # every entry is rounding noise of the size the reference's own r has
-    assert np.isclose(np.linalg.norm(o["r"]), o["residual"], rtol=1e-12, atol=0)
-    assert np.max(np.abs(o["r"])) <= max(4 * np.max(np.abs(w["r"])), 8 * n * EPS * np.max(np.abs(w["b"])))
-
-
-@pytest.mark.parametrize("opts", [(("force_generic", 1),), (("lookahead", 0),), (("force_generic", 1), ("lookahead", 0)),
-                                  (("panel_trsm", 0),), (("panel_trsm", 0), ("force_generic", 1)),
-                                  (("single_launch_sweeps", 0),)])
-def test_kernel_families_and_schedules_agree(ms, opts):
-    """DMMA tiles vs generic DFMA kernel, look-ahead vs in-order: same factor within rounding."""
-    n, m = 640, 128
-    base = gpu_pipeline(ms, n, m)
-    alt = gpu_pipeline(ms, n, m, options=opts)
-    tol = C_TOL * n * EPS * 1.62 * n * n
-    assert rel(np.triu(alt["R"]), np.triu(base["R"])) <= tol
-    assert rel(alt["x"], base["x"]) <= tol
-    if ("lookahead", 0) in opts and ("force_generic", 1) not in opts:
-        assert np.array_equal(alt["R"], base["R"])           # scheduling must not change arithmetic
-
-
-@pytest.mark.parametrize("n,m", [(640, 128), (1024, 256), (2048, 64), (1000, 192)])
-def test_tile_kernel_rank3_and_2d_tma_loads_agree(ms, n, m):
-    """The update launches feed the tile kernel through a rank-3 tensor map over the chunk-major panel
-    buffer (three TMA instructions per stage); "tile_tma3" = 0 selects the twelve 2-D loads that land
-    the same shared-memory image.  Same DMMA sequence per accumulator, so factor and solution must be
-    bit-identical — also with negative d (sign flips) through the dense upload path."""
-    base = gpu_pipeline(ms, n, m)
-    alt = gpu_pipeline(ms, n, m, options=(("tile_tma3", 0),))
-    assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
-    # the order in which the stored tiles are walked (bands of "tile_band_w" column tiles; 64 by default,
-    # i.e. a single band at these n) must not change a bit either: 1 and 3 give many bands here
-    for bw in (1, 3):
-        alt = gpu_pipeline(ms, n, m, options=(("tile_band_w", bw),))
-        assert np.array_equal(alt["R"], base["R"]) and np.array_equal(alt["x"], base["x"])
-    rng = np.random.default_rng(5)
     sign = np.where(np.arange(n) % 7 == 3, -1.0, 1.0)
     L = np.tril(rng.standard_normal((n, n)) * 0.05, -1) + np.eye(n)
     indef = L @ np.diag(sign * (1 + rng.random(n))) @ L.T
@@ -593,6 +511,69 @@ def test_indefinite_and_random_spd_dense(ms, ora):
         x_ref = np.array([1.0 if i % 2 == 0 else 0.0 for i in range(n)])
         assert np.linalg.norm(o["x"] - x_ref) <= C_TOL * n * EPS * cond * np.linalg.norm(x_ref)
     assert np.any(d_ref < 0)
+
+
+def test_internal_blocking_keeps_the_reference_semantics(ms, ora):
+    """On one GPU a caller's m = 64 / 128 is factored in block rows of 256 (ms_stats.block_internal) so that the
+    trailing update runs with K = 256.  R, d, y, x must not depend on that beyond rounding, the exact modes must keep
+    the caller's blocking, and the reference's per-block-row pivot pre-test (src/solver.cpp:117) must still be
+    taken per m rows: a diagonal entry that is 0 in the input but not once the block rows above it have been
+    applied passes with m = 64 (also under the internal 256) and fails with m = 256, exactly like the oracle."""
+    for n, m in [(640, 128), (1000, 64), (300, 64), (2048, 64)]:
+        base = gpu_pipeline(ms, n, m)
+        plain = gpu_pipeline(ms, n, m, options=(("super_block", 0),))
+        exact = gpu_pipeline(ms, n, m, options=(("exact_pivots", 1),))
+        w = ora.solve_pipeline(n, m) if n <= 1000 else None
+        assert base["stats"]["block_internal"] == 256 and plain["stats"]["block_internal"] == m
+        assert exact["stats"]["block_internal"] == m
+        tol = C_TOL * n * EPS * 1.62 * n * n
+        for o in (base, plain):
+            assert not o["factor_fail"] and np.all(o["d"] == 1.0) and o["stats"]["used_dmma"] == 1
+            assert o["stats"]["forward_fused"] == 1
+        assert rel(np.triu(base["R"]), np.triu(plain["R"])) <= tol
+        assert rel(base["y"], plain["y"]) <= tol and rel(base["x"], plain["x"]) <= tol
+        if w is not None:
+            assert rel(np.triu(base["R"]), np.triu(w["R"])) <= tol and rel(base["x"], w["x"]) <= tol
+            assert base["residual"] <= max(2 * w["residual"], 8 * n * EPS * np.linalg.norm(w["b"]))
+    # the pre-test: R = I + small, R[0, 69] = 1, d_69 = -1 -> A[69, 69] = 1 - 1 = 0 in the input, -1 after block row 0
+    n = 256
+    rng = np.random.default_rng(21)
+    R = np.eye(n) + np.triu(rng.standard_normal((n, n)) * 0.01, 1)
+    R[:69, 69] = 0.0
+    R[0, 69] = 1.0
+    d = np.ones(n)
+    d[69] = -1.0
+    A = R.T @ np.diag(d) @ R
+    A[69, 69] = 0.0
+    a = np.triu(A)
+    _, norm = ora.b_norm(a)
+    verdict = {}
+    for m in (64, 128, 256):
+        r_ref, d_ref, f_ref = ora.factor(a, m, norm)
+        verdict[m] = bool(f_ref)
+        for opts in ((), (("super_block", 0),), (("force_generic", 1),)):
+            o = gpu_pipeline(ms, n, m, dense=a, options=opts)
+            assert bool(o["factor_fail"]) == bool(f_ref), (m, opts)
+            if not f_ref:
+                assert np.array_equal(o["d"], d_ref) and d_ref[69] == -1.0
+                assert rel(np.triu(o["R"]), np.triu(r_ref)) <= C_TOL * n * EPS * 1e4
+    assert verdict == {64: False, 128: True, 256: True}
+    # packed layout and row transfers keep speaking the caller's m after a factorisation under the internal blocking
+    n, m = 520, 64
+    with ms.Solver(n, m) as s:
+        s.init_formula(0)
+        fail, _ = s.factor(s.b_and_norm())
+        assert not fail and s.stats()["block_internal"] == 256
+        up = np.triu(s.get_upper())
+        body = np.zeros(n * (n + 1) // 2)
+        s.download_packed(body)
+        for i in (0, 63, 64, 200, 519):
+            for j in (i, min(n - 1, i + 70), n - 1):
+                assert body[ora.packed_offset(i, j, n, m)] == up[i, j]
+        rows = s.download_rows(64, 128)
+        assert np.array_equal(np.triu(rows[:64, 64:]), np.triu(up[64:128, 64:]))
+        assert np.array_equal(np.triu(rows[64:, 128:]), np.triu(up[128:192, 128:]))
+        assert np.all(rows[:64, :64] == 0) and np.all(rows[64:, :128] == 0)   # left of the caller's diagonal block: untouched
 
 
 def test_packed_layout_round_trip(ms, ora):

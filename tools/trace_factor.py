@@ -31,7 +31,8 @@ with ms.Solver(n, m, device=local, rank=rank, nranks=world, unique_id=uid) as s:
         fail, el = s.factor(norm)
     nb = (n + m - 1) // m
     a, b, c = (np.zeros(nb, dtype=np.float32) for _ in range(3))
-    L.ms_debug_trace(s.h, a.ctypes.data_as(fp), b.ctypes.data_as(fp), c.ctypes.data_as(fp), nb)
+    # (a single GPU may walk block rows of 256 for m = 64 / 128: the trace has one entry per INTERNAL block row)
+    nb = L.ms_debug_trace(s.h, a.ctypes.data_as(fp), b.ctypes.data_as(fp), c.ctypes.data_as(fp), nb)
     if rank in (0, world - 1):
         print(f"rank {rank}/{world} n={n} m={m} factor={el*1e3:.1f} ms")
         print(" step  panel_ready  main_done  strip_ready   d_panel  d_main   wait(main_done - next panel)")
