@@ -178,8 +178,11 @@ ms_get_unique_id (void *id128)
   return ms_nccl_unique_id (id128);
 }
 
-extern "C" int
-ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, const void *unique_id)
+static int g_last_device = -1;  // device of the most recent ms_create in this process (blk_ctx follows it)
+
+static int
+create_ctx (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, const void *unique_id,
+            size_t stage_doubles)
 {
   MS_CHECK_ARG (out != nullptr, "out is null");
   *out = nullptr;
@@ -275,7 +278,7 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   CK (cudaMalloc (&c->flags, 8 * sizeof (int)));
   CK (cudaMemset (c->flags, 0, 8 * sizeof (int)));
   CK (cudaHostAlloc (&c->h_flags, 8 * sizeof (int), cudaHostAllocDefault));
-  c->stage_doubles = MS_STAGE_DOUBLES;
+  c->stage_doubles = stage_doubles;
   CK (cudaMalloc (&c->d_stage, 2 * c->stage_doubles * sizeof (double)));
   CK (cudaHostAlloc (&c->h_pinned, 2 * c->stage_doubles * sizeof (double), cudaHostAllocDefault));
 
@@ -323,13 +326,22 @@ ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, c
   if (e && atoi (e))
     c->panel_trsm = false;
   e = getenv ("MS_LEFT_LOOKING");
-  if (e && !atoi (e))
-    c->left_looking = false;
+  if (e)
+    c->left_looking = std::min (2, std::max (0, atoi (e)));
   e = getenv ("MS_NO_LOOKAHEAD");
   if (e && atoi (e))
     c->lookahead = false;
   *out = c;
   return MS_OK;
+}
+
+extern "C" int
+ms_create (ms_ctx **out, size_t n, size_t m, int device, int rank, int nranks, const void *unique_id)
+{
+  int r = create_ctx (out, n, m, device, rank, nranks, unique_id, MS_STAGE_DOUBLES);
+  if (r == MS_OK)
+    g_last_device = device;
+  return r;
 }
 
 extern "C" int
@@ -360,7 +372,7 @@ ms_set_option (ms_ctx *c, const char *key, long value)
   else if (!strcmp (key, "panel_trsm"))
     c->panel_trsm = value != 0;
   else if (!strcmp (key, "left_looking"))
-    c->left_looking = value != 0;
+    c->left_looking = (int)std::min (2l, std::max (0l, value));
   else if (!strcmp (key, "single_launch_sweeps"))
     c->no_sweep = value == 0;
   else if (!strcmp (key, "fuse_forward"))
@@ -872,7 +884,7 @@ factor_block_row (ms_ctx *c, size_t I, int pb, double thresh, cudaStream_t s, cu
       // block rows brings all of that block row's rows up to date (they are pre-tested with it, see above); the
       // pieces after it then only lack the pieces of their own caller block row.  The exact-arithmetic kernels keep
       // the right-looking order.
-      const bool left = tiles && c->left_looking;
+      const bool left = tiles && (c->left_looking == 2 || (c->left_looking == 1 && c->ncols - I * c->m >= MS_LEFT_MIN_COLS));
       if (left && k0 > 0)
         {
           const size_t ksub = k0 / c->m_api * c->m_api;
@@ -1274,11 +1286,16 @@ blk_ctx (ms_ctx **out)
   std::lock_guard<std::mutex> lk (g_blk_mu);
   if (!g_blk)
     {
-      int dev = 0;
-      const char *e = getenv ("MS_DEVICE");
-      if (e)
-        dev = atoi (e);
-      int r = ms_create (&g_blk, 64, 64, dev, 0, 1, nullptr);
+      // on the device of the context this process created last (a rank of an MS_NGPU run works on its own GPU;
+      // round 1 opened an extra CUDA context on GPU 0 from every rank), else MS_DEVICE, else 0.  The block
+      // routines stage through buffers of their own, so this context carries the smallest staging area.
+      int dev = g_last_device;
+      if (dev < 0)
+        {
+          const char *e = getenv ("MS_DEVICE");
+          dev = e ? atoi (e) : 0;
+        }
+      int r = create_ctx (&g_blk, 64, 64, dev, 0, 1, nullptr, (size_t)1 << 16);
       if (r < 0)
         return r;
       // the block API mirrors the reference's routines one to one: its diagonal-block factor keeps the

@@ -64,6 +64,11 @@ round_up (size_t v, size_t a)
   return (v + a - 1) / a * a;
 }
 
+// Left-looking in-block updates from this many remaining columns on: below it the right-looking strips (<= 3 row
+// tiles x r/128 column tiles at K = 64) fit one wave of CTAs and are the shorter chain (n = 4096: 4.23 vs 4.45 ms);
+// above it the deeper, smaller launches win (n = 16384: 52.4 vs 52.7 ms, n = 65536: 2817.5 vs 2822.1 ms).
+constexpr size_t MS_LEFT_MIN_COLS = 8192;
+
 // One piece = up to MS_SUB consecutive rows inside one block row.
 struct ms_piece
 {
@@ -102,9 +107,10 @@ struct ms_ctx
   bool profile_update = false;
   bool trace = false;       // MS_TRACE=1: timing-enabled step events, read back by ms_debug_trace
   std::vector<float> trace_panel, trace_free, trace_strip;
-  bool left_looking = true; // inside a block row the tensor-core path updates each 64-row piece just before it is
+  int left_looking = 1;     // inside a block row the tensor-core path can update each 64-row piece just before it is
                             // factored, with all pieces above it at once (K = 64, 128, 192) — instead of pushing every
-                            // factored piece into all rows below it (K = 64 each time); "left_looking" option
+                            // factored piece into all rows below it (K = 64 each time).  0 = never, 2 = always,
+                            // 1 = where it pays: block rows with at least MS_LEFT_MIN_COLS columns ("left_looking" option)
   bool panel_trsm = true;   // K3 as a triangular solve (default) or as a DMMA product with the inverse
 
   double *A = nullptr;       // rows_alloc x ld, row-major; only j >= i meaningful

@@ -342,9 +342,20 @@ strip_factor (double (&c)[DIAG_NB][2], int i0, int h, int lane, double thresh, d
             {
               // r(row, k), k = i0 + u, lives in the lane that owns column k
               const double rk = __shfl_sync (0xffffffffu, LO ? c[t][0] : c[t][1], (i0 + u) & 31);
-              if (LO)
-                c[u][0] = __dsub_rn (c[u][0], __dmul_rn (__dmul_rn (rk, c[t][0]), di));
-              c[u][1] = __dsub_rn (c[u][1], __dmul_rn (__dmul_rn (rk, c[t][1]), di));
+              if (FAST)
+                {
+                  // one FMA per element on the pivot chain (d_i = +-1: the product with it is exact)
+                  const double mk = -(rk * di);
+                  if (LO)
+                    c[u][0] = fma (mk, c[t][0], c[u][0]);
+                  c[u][1] = fma (mk, c[t][1], c[u][1]);
+                }
+              else
+                {
+                  if (LO)
+                    c[u][0] = __dsub_rn (c[u][0], __dmul_rn (__dmul_rn (rk, c[t][0]), di));
+                  c[u][1] = __dsub_rn (c[u][1], __dmul_rn (__dmul_rn (rk, c[t][1]), di));
+                }
             }
         }
     }
@@ -378,18 +389,33 @@ diag_strip_kernel (double *__restrict__ blk, size_t ld, int h, double thresh, do
   const int tx = tid & 15, ty = tid >> 4;
   const int lane = tid & 31, warp = tid >> 5;
 
-  // the reference's pre-update pivot test (src/solver.cpp:117) for the whole block row
-  for (int i = tid; i < pre_count; i += 256)
-    if (fabs (pre_diag[(size_t)i * pre_ld + i]) < thresh)
-      flags[0] = 1;
-
-  for (int i = ty; i < MS_SUB; i += 16)
-    for (int j = tx; j < MS_SUB; j += 16)
+  // The block first, all 16 loads of a thread in flight at once (the rolled loop of round 1 paid several global
+  // round trips here: 4900 cycles of a 44 000-cycle kernel, profiles/r02_diag_timing.txt), then the reference's
+  // pre-update pivot test (src/solver.cpp:117) for the block row, whose loads overlap them.
+  double stage[16];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int q = 0; q < 4; q++)
       {
-        a[i * S + j] = (i < h && j < h && j >= i) ? blk[(size_t)i * ld + j] : 0.0;
+        const int i = ty + 16 * r, j = tx + 16 * q;
+        stage[r * 4 + q] = (i < h && j < h && j >= i) ? blk[(size_t)i * ld + j] : 0.0;
+      }
+  bool pre_bad = false;
+  for (int i = tid; i < pre_count; i += 256)
+    pre_bad |= fabs (pre_diag[(size_t)i * pre_ld + i]) < thresh;
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      {
+        const int i = ty + 16 * r, j = tx + 16 * q;
+        a[i * S + j] = stage[r * 4 + q];
         if (want_inverse)
           v[i * S + j] = 0.0;
       }
+  if (pre_bad)
+    flags[0] = 1;
   __syncthreads ();
   if (cyc)
     tc1 = clock64 ();
@@ -717,6 +743,83 @@ trsm_panel_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restri
     }
 }
 
+// The same solve with FOUR threads per column (default since round 2).  The kernel above is a single instruction
+// stream of ~3500 instructions per column; with one or two warps per scheduler it runs at the issue rate of a lone
+// warp (one instruction every 4-6 cycles, profiles/r02_latency_probe.txt) and takes 20 us however few columns
+// there are — it sits on the panel chain four times per block row.  Here the quad of lanes 4c .. 4c+3 shares
+// column c: lane t keeps rows k = t (mod 4) of it (16 values) in registers, and the solve runs right-looking,
+//     step i:  x_i = a_i / R_ii  (lane i mod 4)  ->  quad broadcast  ->  a_k -= R_ik x_i  for the lane's own k > i,
+// so a lane issues ~1100 instructions (544 FMAs, 16-byte broadcast loads of R out of a lane-major, padded
+// shared-memory image) and the dependent chain per step is multiply + shuffle + FMA.  Every a_k receives its
+// products in ascending i with single FMAs — plain forward substitution, one rounding per product.
+// 256 threads = 64 columns per CTA; a warp touches 4 rows x 8 consecutive columns per load/store (whole sectors).
+constexpr int TQ_STRIDE = 18;  // doubles per (step, lane-of-quad) row of the R image: 16 + 2 keeps the four lanes'
+                               // 16-byte loads in different banks
+__global__ void __launch_bounds__ (256, 3)
+trsm_quad_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restrict__ rows, size_t ld, int h, size_t col_lo,
+                  size_t n, const double *__restrict__ dpiece, double *__restrict__ PB, size_t pb_H, size_t pb_k0)
+{
+  // Rq[(i * 4 + t) * TQ_STRIDE + kk] = R(i, 4 kk + t) where 4 kk + t > i (and both < h), 0 elsewhere
+  __shared__ __align__ (16) double Rq[MS_SUB * 4 * TQ_STRIDE];
+  __shared__ double rinv[MS_SUB], ds[MS_SUB];
+  const int t = threadIdx.x & 3;
+  const size_t j = col_lo + (size_t)blockIdx.x * 64 + (threadIdx.x >> 2);
+  const bool live = j < n;
+  // the lane's 16 values first: all loads are in flight while R is staged
+  double a[16];
+#pragma unroll
+  for (int kk = 0; kk < 16; kk++)
+    {
+      const int k = 4 * kk + t;
+      a[kk] = (live && k < h) ? rows[(size_t)k * ld + j] : 0.0;
+    }
+  for (int e = threadIdx.x; e < MS_SUB * MS_SUB; e += 256)
+    {
+      const int i = e >> 6, k = e & 63;  // coalesced read of row i of R
+      Rq[(i * 4 + (k & 3)) * TQ_STRIDE + (k >> 2)] = (k > i && k < h) ? Rblk[(size_t)i * ldr + k] : 0.0;
+    }
+  if (threadIdx.x < MS_SUB)
+    {
+      const int i = threadIdx.x;
+      rinv[i] = i < h ? 1.0 / Rblk[(size_t)i * ldr + i] : 1.0;
+      ds[i] = i < h ? dpiece[i] : 1.0;
+    }
+  __syncthreads ();
+#pragma unroll
+  for (int i = 0; i < MS_SUB; i++)
+    {
+      const int q = i >> 2, o = i & 3;
+      double xi = a[q] * rinv[i];                       // meaningful on lane o of the quad only
+      xi = __shfl_sync (0xffffffffu, xi, o, 4);
+      if (t == o)
+        a[q] = xi;                                      // a_i is final: it now holds x_i
+      const double *rrow = &Rq[(i * 4 + t) * TQ_STRIDE];
+#pragma unroll
+      for (int kk = (q & ~1); kk < 16; kk += 2)
+        {
+          const double2 r2 = *reinterpret_cast<const double2 *> (rrow + kk);
+          if (kk >= q)
+            a[kk] = fma (-r2.x, xi, a[kk]);              // R image is 0 for k <= i: x_i itself and finished rows stay
+          a[kk + 1] = fma (-r2.y, xi, a[kk + 1]);
+        }
+    }
+  if (!live)
+    return;
+  double *pcol = rows + j;
+  double *ppb = PB + chunk_major_index (pb_k0, j, pb_H);
+#pragma unroll
+  for (int kk = 0; kk < 16; kk++)
+    {
+      const int k = 4 * kk + t;
+      if (k < h)
+        {
+          const double val = a[kk] * ds[k];
+          pcol[(size_t)k * ld] = val;
+          ppb[(size_t)k * MS_CHUNK] = val;               // k-th row of the same 16-column chunk
+        }
+    }
+}
+
 int
 ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t ld, int h, size_t col_lo, size_t n,
                  const double *dpiece, double *PB, size_t pb_H, size_t pb_k0, cudaStream_t s)
@@ -724,6 +827,20 @@ ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t
   if (col_lo >= n)
     return MS_OK;
   MS_CHECK_ARG (h >= 1 && h <= MS_SUB, "trsm panel piece must have 1..64 rows");
+  static int quad = -1;  // MS_TRSM_QUAD=0 selects the one-thread-per-column kernel (A/B, profiles/README.md)
+  if (quad < 0)
+    {
+      const char *e = getenv ("MS_TRSM_QUAD");
+      quad = (e && !atoi (e)) ? 0 : 1;
+    }
+  if (quad)
+    {
+      trsm_quad_kernel<<<(unsigned)((n - col_lo + 63) / 64), 256, 0, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H,
+                                                                           pb_k0);
+      LAUNCH_COUNT (c);
+      MS_CUDA (cudaGetLastError ());
+      return MS_OK;
+    }
   unsigned grid = (unsigned)((n - col_lo + 127) / 128);
   const size_t smem = (size_t)MS_SUB * 128 * sizeof (double);
   static bool configured_dev[64] = {};

@@ -279,7 +279,8 @@ def test_pipeline_against_oracle_formula_sweep(ms, ora, n, m):
 
 @pytest.mark.parametrize("opts", [(("force_generic", 1),), (("lookahead", 0),), (("force_generic", 1), ("lookahead", 0)),
                                   (("panel_trsm", 0),), (("panel_trsm", 0), ("force_generic", 1)),
-                                  (("single_launch_sweeps", 0),)])
+                                  (("single_launch_sweeps", 0),), (("left_looking", 0),), (("left_looking", 2),),
+                                  (("left_looking", 2), ("super_block", 0))])
 def test_kernel_families_and_schedules_agree(ms, opts):
     """DMMA tiles vs generic DFMA kernel, look-ahead vs in-order: same factor within rounding."""
     n, m = 640, 128
