@@ -820,6 +820,81 @@ trsm_quad_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restric
     }
 }
 
+// The quad solve as a LOOP.  Measured on the B200 (profiles/README.md): the fully unrolled kernels above take 18-20 us
+// per launch however few columns there are, although their dependent chains are ~2 us long — every warp runs
+// through 24-80 KB of straight-line code exactly once, so the launch is bound by cold instruction fetch.  Here
+// the 16 groups of four steps are one rolled loop of ~170 instructions: the lane's register window a[0..15]
+// always starts at the current group (after a group its finished value is written out and the window shifts by
+// one), and the shared-memory image of R is stored pre-shifted the same way, so that every iteration indexes
+// registers and R identically.  Each step runs all 16 FMAs (R image 0 beyond row 63): 1024 instead of 544 per
+// lane, all of them out of the instruction cache.
+__global__ void __launch_bounds__ (256, 2)
+trsm_quad_loop_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restrict__ rows, size_t ld, int h,
+                       size_t col_lo, size_t n, const double *__restrict__ dpiece, double *__restrict__ PB, size_t pb_H,
+                       size_t pb_k0)
+{
+  // Rq[(i * 4 + t) * TQ_STRIDE + kk] = R(i, k), k = 4 (i / 4 + kk) + t, where i < k < h (k <= 63), 0 elsewhere
+  __shared__ __align__ (16) double Rq[MS_SUB * 4 * TQ_STRIDE];
+  __shared__ double rinv[MS_SUB], ds[MS_SUB];
+  const int t = threadIdx.x & 3;
+  const size_t j = col_lo + (size_t)blockIdx.x * 64 + (threadIdx.x >> 2);
+  const bool live = j < n;
+  double a[16];
+#pragma unroll
+  for (int kk = 0; kk < 16; kk++)
+    {
+      const int k = 4 * kk + t;
+      a[kk] = (live && k < h) ? rows[(size_t)k * ld + j] : 0.0;
+    }
+  for (int e = threadIdx.x; e < MS_SUB * MS_SUB; e += 256)
+    {
+      const int i = e >> 6, rem = e & 63;
+      const int k = 4 * (i >> 2) + rem;  // consecutive threads read consecutive entries of row i of R
+      Rq[(i * 4 + (rem & 3)) * TQ_STRIDE + (rem >> 2)] = (k < MS_SUB && k > i && k < h) ? Rblk[(size_t)i * ldr + k] : 0.0;
+    }
+  if (threadIdx.x < MS_SUB)
+    {
+      const int i = threadIdx.x;
+      rinv[i] = i < h ? 1.0 / Rblk[(size_t)i * ldr + i] : 1.0;
+      ds[i] = i < h ? dpiece[i] : 1.0;
+    }
+  __syncthreads ();
+  double *pcol = rows + j;
+  double *ppb = PB + chunk_major_index (pb_k0, live ? j : col_lo, pb_H);
+#pragma unroll 1
+  for (int q = 0; q < 16; q++)
+    {
+#pragma unroll
+      for (int o = 0; o < 4; o++)
+        {
+          const int i = 4 * q + o;
+          double xi = a[0] * rinv[i];                    // meaningful on lane o of the quad only
+          xi = __shfl_sync (0xffffffffu, xi, o, 4);
+          if (t == o)
+            a[0] = xi;                                   // a_i is final: it now holds x_i
+          const double *rrow = &Rq[(i * 4 + t) * TQ_STRIDE];
+#pragma unroll
+          for (int kk = 0; kk < 16; kk += 2)
+            {
+              const double2 r2 = *reinterpret_cast<const double2 *> (rrow + kk);
+              a[kk] = fma (-r2.x, xi, a[kk]);            // the image is 0 for k <= i: finished values stay
+              a[kk + 1] = fma (-r2.y, xi, a[kk + 1]);
+            }
+        }
+      const int k = 4 * q + t;
+      if (live && k < h)
+        {
+          const double val = a[0] * ds[k];
+          pcol[(size_t)k * ld] = val;
+          ppb[(size_t)k * MS_CHUNK] = val;               // k-th row of the same 16-column chunk
+        }
+#pragma unroll
+      for (int kk = 0; kk < 15; kk++)
+        a[kk] = a[kk + 1];
+      a[15] = 0.0;
+    }
+}
+
 int
 ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t ld, int h, size_t col_lo, size_t n,
                  const double *dpiece, double *PB, size_t pb_H, size_t pb_k0, cudaStream_t s)
@@ -827,16 +902,19 @@ ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t
   if (col_lo >= n)
     return MS_OK;
   MS_CHECK_ARG (h >= 1 && h <= MS_SUB, "trsm panel piece must have 1..64 rows");
-  static int quad = -1;  // MS_TRSM_QUAD=0 selects the one-thread-per-column kernel (A/B, profiles/README.md)
+  static int quad = -1;  // MS_TRSM_QUAD: 2 = quad solve as a loop (default), 1 = unrolled quad solve, 0 = one thread per column
   if (quad < 0)
     {
       const char *e = getenv ("MS_TRSM_QUAD");
-      quad = (e && !atoi (e)) ? 0 : 1;
+      quad = e ? std::min (2, std::max (0, atoi (e))) : 2;
     }
   if (quad)
     {
-      trsm_quad_kernel<<<(unsigned)((n - col_lo + 63) / 64), 256, 0, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H,
-                                                                           pb_k0);
+      const unsigned g = (unsigned)((n - col_lo + 63) / 64);
+      if (quad == 2)
+        trsm_quad_loop_kernel<<<g, 256, 0, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H, pb_k0);
+      else
+        trsm_quad_kernel<<<g, 256, 0, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H, pb_k0);
       LAUNCH_COUNT (c);
       MS_CUDA (cudaGetLastError ());
       return MS_OK;
