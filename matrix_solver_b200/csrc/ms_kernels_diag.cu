@@ -743,91 +743,23 @@ trsm_panel_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restri
     }
 }
 
-// The same solve with FOUR threads per column (default since round 2).  The kernel above is a single instruction
-// stream of ~3500 instructions per column; with one or two warps per scheduler it runs at the issue rate of a lone
-// warp (one instruction every 4-6 cycles, profiles/r02_latency_probe.txt) and takes 20 us however few columns
-// there are — it sits on the panel chain four times per block row.  Here the quad of lanes 4c .. 4c+3 shares
-// column c: lane t keeps rows k = t (mod 4) of it (16 values) in registers, and the solve runs right-looking,
+// The same solve with FOUR threads per column.  The kernel above is a single stream of ~3500 instructions per
+// column and takes 20 us however few columns there are — it sits on the panel chain four times per block row.
+// Here the quad of lanes 4c .. 4c+3 shares column c: lane t keeps rows k = t (mod 4) of it (16 values) in
+// registers, and the solve runs right-looking,
 //     step i:  x_i = a_i / R_ii  (lane i mod 4)  ->  quad broadcast  ->  a_k -= R_ik x_i  for the lane's own k > i,
-// so a lane issues ~1100 instructions (544 FMAs, 16-byte broadcast loads of R out of a lane-major, padded
-// shared-memory image) and the dependent chain per step is multiply + shuffle + FMA.  Every a_k receives its
-// products in ascending i with single FMAs — plain forward substitution, one rounding per product.
-// 256 threads = 64 columns per CTA; a warp touches 4 rows x 8 consecutive columns per load/store (whole sectors).
+// so the dependent chain per step is multiply + shuffle + FMA, and every a_k receives its products in ascending
+// i with single FMAs — plain forward substitution, one rounding per product.  256 threads = 64 columns per CTA;
+// a warp touches 4 rows x 8 consecutive columns per load/store (whole sectors).
+// The 16 groups of four steps are ONE rolled loop of ~170 instructions: the lane's register window a[0..15] always
+// starts at the current group (after a group its finished value is written out and the window shifts by one), and
+// the shared-memory image of R is stored pre-shifted the same way, so every iteration indexes registers and R
+// identically; each step runs all 16 FMAs (the image is 0 beyond row 63).  (A fully unrolled variant, 544 FMAs in
+// 1500 instructions, measured the same 18 us as the loop: see profiles/README.md.)
+// All global loads of a thread — its 16 values, its 16 entries of R, the diagonal — are issued before the first
+// of them is used.
 constexpr int TQ_STRIDE = 18;  // doubles per (step, lane-of-quad) row of the R image: 16 + 2 keeps the four lanes'
                                // 16-byte loads in different banks
-__global__ void __launch_bounds__ (256, 3)
-trsm_quad_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restrict__ rows, size_t ld, int h, size_t col_lo,
-                  size_t n, const double *__restrict__ dpiece, double *__restrict__ PB, size_t pb_H, size_t pb_k0)
-{
-  // Rq[(i * 4 + t) * TQ_STRIDE + kk] = R(i, 4 kk + t) where 4 kk + t > i (and both < h), 0 elsewhere
-  __shared__ __align__ (16) double Rq[MS_SUB * 4 * TQ_STRIDE];
-  __shared__ double rinv[MS_SUB], ds[MS_SUB];
-  const int t = threadIdx.x & 3;
-  const size_t j = col_lo + (size_t)blockIdx.x * 64 + (threadIdx.x >> 2);
-  const bool live = j < n;
-  // the lane's 16 values first: all loads are in flight while R is staged
-  double a[16];
-#pragma unroll
-  for (int kk = 0; kk < 16; kk++)
-    {
-      const int k = 4 * kk + t;
-      a[kk] = (live && k < h) ? rows[(size_t)k * ld + j] : 0.0;
-    }
-  for (int e = threadIdx.x; e < MS_SUB * MS_SUB; e += 256)
-    {
-      const int i = e >> 6, k = e & 63;  // coalesced read of row i of R
-      Rq[(i * 4 + (k & 3)) * TQ_STRIDE + (k >> 2)] = (k > i && k < h) ? Rblk[(size_t)i * ldr + k] : 0.0;
-    }
-  if (threadIdx.x < MS_SUB)
-    {
-      const int i = threadIdx.x;
-      rinv[i] = i < h ? 1.0 / Rblk[(size_t)i * ldr + i] : 1.0;
-      ds[i] = i < h ? dpiece[i] : 1.0;
-    }
-  __syncthreads ();
-#pragma unroll
-  for (int i = 0; i < MS_SUB; i++)
-    {
-      const int q = i >> 2, o = i & 3;
-      double xi = a[q] * rinv[i];                       // meaningful on lane o of the quad only
-      xi = __shfl_sync (0xffffffffu, xi, o, 4);
-      if (t == o)
-        a[q] = xi;                                      // a_i is final: it now holds x_i
-      const double *rrow = &Rq[(i * 4 + t) * TQ_STRIDE];
-#pragma unroll
-      for (int kk = (q & ~1); kk < 16; kk += 2)
-        {
-          const double2 r2 = *reinterpret_cast<const double2 *> (rrow + kk);
-          if (kk >= q)
-            a[kk] = fma (-r2.x, xi, a[kk]);              // R image is 0 for k <= i: x_i itself and finished rows stay
-          a[kk + 1] = fma (-r2.y, xi, a[kk + 1]);
-        }
-    }
-  if (!live)
-    return;
-  double *pcol = rows + j;
-  double *ppb = PB + chunk_major_index (pb_k0, j, pb_H);
-#pragma unroll
-  for (int kk = 0; kk < 16; kk++)
-    {
-      const int k = 4 * kk + t;
-      if (k < h)
-        {
-          const double val = a[kk] * ds[k];
-          pcol[(size_t)k * ld] = val;
-          ppb[(size_t)k * MS_CHUNK] = val;               // k-th row of the same 16-column chunk
-        }
-    }
-}
-
-// The quad solve as a LOOP.  Measured on the B200 (profiles/README.md): the fully unrolled kernels above take 18-20 us
-// per launch however few columns there are, although their dependent chains are ~2 us long — every warp runs
-// through 24-80 KB of straight-line code exactly once, so the launch is bound by cold instruction fetch.  Here
-// the 16 groups of four steps are one rolled loop of ~170 instructions: the lane's register window a[0..15]
-// always starts at the current group (after a group its finished value is written out and the window shifts by
-// one), and the shared-memory image of R is stored pre-shifted the same way, so that every iteration indexes
-// registers and R identically.  Each step runs all 16 FMAs (R image 0 beyond row 63): 1024 instead of 544 per
-// lane, all of them out of the instruction cache.
 __global__ void __launch_bounds__ (256, 2)
 trsm_quad_loop_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restrict__ rows, size_t ld, int h,
                        size_t col_lo, size_t n, const double *__restrict__ dpiece, double *__restrict__ PB, size_t pb_H,
@@ -846,17 +778,32 @@ trsm_quad_loop_kernel (const double *__restrict__ Rblk, size_t ldr, double *__re
       const int k = 4 * kk + t;
       a[kk] = (live && k < h) ? rows[(size_t)k * ld + j] : 0.0;
     }
-  for (int e = threadIdx.x; e < MS_SUB * MS_SUB; e += 256)
+  double rr[16];
+#pragma unroll
+  for (int u = 0; u < 16; u++)
     {
+      const int e = threadIdx.x + 256 * u;
       const int i = e >> 6, rem = e & 63;
       const int k = 4 * (i >> 2) + rem;  // consecutive threads read consecutive entries of row i of R
-      Rq[(i * 4 + (rem & 3)) * TQ_STRIDE + (rem >> 2)] = (k < MS_SUB && k > i && k < h) ? Rblk[(size_t)i * ldr + k] : 0.0;
+      rr[u] = (k < MS_SUB && k > i && k < h) ? Rblk[(size_t)i * ldr + k] : 0.0;
+    }
+  double rdiag = 1.0, dval = 1.0;
+  if (threadIdx.x < MS_SUB && (int)threadIdx.x < h)
+    {
+      rdiag = Rblk[(size_t)threadIdx.x * ldr + threadIdx.x];
+      dval = dpiece[threadIdx.x];
+    }
+#pragma unroll
+  for (int u = 0; u < 16; u++)
+    {
+      const int e = threadIdx.x + 256 * u;
+      const int i = e >> 6, rem = e & 63;
+      Rq[(i * 4 + (rem & 3)) * TQ_STRIDE + (rem >> 2)] = rr[u];
     }
   if (threadIdx.x < MS_SUB)
     {
-      const int i = threadIdx.x;
-      rinv[i] = i < h ? 1.0 / Rblk[(size_t)i * ldr + i] : 1.0;
-      ds[i] = i < h ? dpiece[i] : 1.0;
+      rinv[threadIdx.x] = 1.0 / rdiag;
+      ds[threadIdx.x] = dval;
     }
   __syncthreads ();
   double *pcol = rows + j;
@@ -902,19 +849,16 @@ ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t
   if (col_lo >= n)
     return MS_OK;
   MS_CHECK_ARG (h >= 1 && h <= MS_SUB, "trsm panel piece must have 1..64 rows");
-  static int quad = -1;  // MS_TRSM_QUAD: 2 = quad solve as a loop (default), 1 = unrolled quad solve, 0 = one thread per column
+  static int quad = -1;  // MS_TRSM_QUAD=0 selects the one-thread-per-column kernel
   if (quad < 0)
     {
       const char *e = getenv ("MS_TRSM_QUAD");
-      quad = e ? std::min (2, std::max (0, atoi (e))) : 2;
+      quad = (e && !atoi (e)) ? 0 : 1;
     }
   if (quad)
     {
       const unsigned g = (unsigned)((n - col_lo + 63) / 64);
-      if (quad == 2)
-        trsm_quad_loop_kernel<<<g, 256, 0, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H, pb_k0);
-      else
-        trsm_quad_kernel<<<g, 256, 0, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H, pb_k0);
+      trsm_quad_loop_kernel<<<g, 256, 0, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H, pb_k0);
       LAUNCH_COUNT (c);
       MS_CUDA (cudaGetLastError ());
       return MS_OK;
