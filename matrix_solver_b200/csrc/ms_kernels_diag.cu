@@ -755,9 +755,10 @@ trsm_panel_kernel (const double *__restrict__ Rblk, size_t ldr, double *__restri
 // starts at the current group (after a group its finished value is written out and the window shifts by one), and
 // the shared-memory image of R is stored pre-shifted the same way, so every iteration indexes registers and R
 // identically; each step runs all 16 FMAs (the image is 0 beyond row 63).  (A fully unrolled variant, 544 FMAs in
-// 1500 instructions, measured the same 18 us as the loop: see profiles/README.md.)
-// All global loads of a thread — its 16 values, its 16 entries of R, the diagonal — are issued before the first
-// of them is used.
+// 1500 instructions, measured the same as the loop.)  All global loads of a thread — its 16 values, its 16 entries
+// of R, the diagonal — are issued before the first of them is used: with the staging loop rolled the isolated
+// launch took 19.7 us, with the loads batched 14.9 us.
+constexpr size_t MS_TRSM_QUAD_MAX_COLS = 8192;
 constexpr int TQ_STRIDE = 18;  // doubles per (step, lane-of-quad) row of the R image: 16 + 2 keeps the four lanes'
                                // 16-byte loads in different banks
 __global__ void __launch_bounds__ (256, 2)
@@ -849,13 +850,18 @@ ms_k_trsm_panel (ms_ctx *c, const double *Rblk, size_t ldr, double *rows, size_t
   if (col_lo >= n)
     return MS_OK;
   MS_CHECK_ARG (h >= 1 && h <= MS_SUB, "trsm panel piece must have 1..64 rows");
-  static int quad = -1;  // MS_TRSM_QUAD=0 selects the one-thread-per-column kernel
+  // Two kernels, chosen by the number of columns: up to MS_TRSM_QUAD_MAX_COLS the launch is a handful of CTAs on an
+  // otherwise waiting chain and the four-threads-per-column kernel is the shorter one (isolated 14.9 against 19.9 us;
+  // n = 4096: 3.95 against 4.07 ms for the whole factorisation); on wide panels its 1024 FMAs per lane and four times
+  // as many CTAs cost the concurrently running trailing update more than the shorter chain returns (n = 16384:
+  // 53.1 against 52.1 ms, n = 65536: 2837 against 2815 ms; profiles/r02_trsm_ab.txt).  MS_TRSM_QUAD=0 / 1 forces one.
+  static int quad = -1;
   if (quad < 0)
     {
       const char *e = getenv ("MS_TRSM_QUAD");
-      quad = (e && !atoi (e)) ? 0 : 1;
+      quad = e ? (atoi (e) ? 1 : 0) : 2;
     }
-  if (quad)
+  if (quad == 1 || (quad == 2 && n - col_lo <= MS_TRSM_QUAD_MAX_COLS))
     {
       const unsigned g = (unsigned)((n - col_lo + 63) / 64);
       trsm_quad_loop_kernel<<<g, 256, 0, s>>> (Rblk, ldr, rows, ld, h, col_lo, n, dpiece, PB, pb_H, pb_k0);

@@ -1,9 +1,10 @@
 #!/bin/bash
-# 2-GPU call Q: the 2-rank tests and the headline at N = 2 on HEAD
+# 2-GPU call Q: every GPU test (incl. the 2-rank ones), smoke and the headline at N = 2 on HEAD
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_multi.py -x -q -m gpu > gpurun_out/r02q_pytest_multi.log 2>&1
-echo "pytest rc=$?"; tail -3 gpurun_out/r02q_pytest_multi.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r02q_pytest_gpu.log 2>&1
+echo "pytest rc=$?"; tail -3 gpurun_out/r02q_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 timeout 400 $TR --nproc-per-node 2 --master-port 29591 bench.py --gpus 2 --steps 3 --warmup 3 --e2e-steps 2 --no-cpu --no-dgemm 2> gpurun_out/r02q_c5_n2.err | tail -1 > gpurun_out/r02q_c5_n2.json
 python - <<'PY'
