@@ -39,6 +39,29 @@ def test_library_exports_every_declared_symbol():
     assert sorted(capi.EXPORTED) == names, "python binding and header disagree"
 
 
+def test_ms_stats_layout_matches_the_python_binding(tmp_path):
+    """ms_stats crosses the ABI by value into a caller-owned struct: the ctypes mirror must have the header's
+    fields at the header's offsets (a field appended on one side only would corrupt the caller's stack)."""
+    fields = [name for name, _ in capi.Stats._fields_]
+    src = tmp_path / "stats_layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {',
+             '  printf("sizeof %zu\\n", sizeof(ms_stats));']
+    lines += [f'  printf("{f} %zu %zu\\n", offsetof(ms_stats, {f}), sizeof(((ms_stats *)0)->{f}));' for f in fields]
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "stats_layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert int(out[0].split()[1]) == ctypes.sizeof(capi.Stats)
+    for line, (name, ctype) in zip(out[1:], capi.Stats._fields_):
+        f, off, size = line.split()
+        assert f == name and int(off) == getattr(capi.Stats, name).offset and int(size) == ctypes.sizeof(ctype), line
+    # and every field of the header is mirrored: the struct body names exactly these members
+    body = re.search(r"typedef struct ms_stats\s*\{(.*?)\}\s*ms_stats;", re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S), re.S).group(1)
+    declared = re.findall(r"\b([a-z_0-9]+)\s*[;,]", body)
+    assert declared == fields
+
+
 def test_no_cpu_fallback():
     _ensure_lib()
     import torch
