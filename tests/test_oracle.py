@@ -209,3 +209,50 @@ def test_reference_values_do_not_depend_on_rank_count():
         many = ol.ref_dump(30, 9, np_ranks=p)
         for k in ("b", "d", "y", "x", "r", "R"):
             assert np.array_equal(one[k], many[k]), (p, k)
+
+
+class _OracleBackedSolver:
+    """What selfcheck.check_parity needs from a Solver, served from an oracle run."""
+
+    def __init__(self, w):
+        self.w = w
+
+    def get_row(self, i):
+        return np.triu(self.w["R"])[i].copy()
+
+    def get_vec(self, which):
+        return self.w[which].copy()
+
+
+@pytest.mark.parametrize("n,m", [(200, 64), (777, 128), (1024, 256)])
+def test_the_bench_self_check_accepts_the_oracle_and_rejects_a_damaged_factor(n, m):
+    """bench.py's `parity` block (matrix_solver_b200/selfcheck.py) is the only factor check at the sizes no CPU run
+    reaches, so the checker itself is checked here: fed with the oracle's R, d, x for the formula matrix it must
+    pass, and it must fail when one entry of one checked row, one d or the norm is off."""
+    from matrix_solver_b200 import selfcheck
+    o = ol.Oracle()
+    w = o.solve_pipeline(n, m)
+    fake = _OracleBackedSolver(w)
+    for world in (1, 2, 8):
+        rows = selfcheck.parity_rows(n, m, world)
+        assert rows == sorted(set(rows)) and rows[0] == 0 and rows[-1] == n - 1 and len(rows) >= 48
+        for r in (m - 1, m, 63, 64):
+            assert r >= n or r in rows          # both sides of block-row and piece boundaries
+    res = selfcheck.check_parity(fake, n, m, 1, w["norm"], False)
+    assert res["ok"] and res["norm_exact"] and res["d_all_plus_one"] and res["r_max_rel"] < 1e-9
+    assert not selfcheck.check_parity(fake, n, m, 1, w["norm"], True)["ok"]            # a reported failure
+    assert not selfcheck.check_parity(fake, n, m, 1, w["norm"] + 1.0, False)["ok"]     # wrong norm
+    row = selfcheck.parity_rows(n, m, 1)[7]
+    bad = dict(w)
+    bad["R"] = w["R"].copy()
+    bad["R"][row, row] *= 1.0 + 1e-5            # (the bound is on max|R - R_ref| / max|R_ref| per row)
+    out = selfcheck.check_parity(_OracleBackedSolver(bad), n, m, 1, w["norm"], False)
+    assert not out["ok"] and out["r_worst_row"] == row
+    bad = dict(w)
+    bad["d"] = w["d"].copy()
+    bad["d"][n // 2] = -1.0
+    assert not selfcheck.check_parity(_OracleBackedSolver(bad), n, m, 1, w["norm"], False)["ok"]
+    bad = dict(w)
+    bad["x"] = w["x"].copy()
+    bad["x"][3] += 0.5
+    assert not selfcheck.check_parity(_OracleBackedSolver(bad), n, m, 1, w["norm"], False)["ok"]
